@@ -1,0 +1,132 @@
+"""Pin the CPU oracle (oracle/d2r_oracle.py) against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py), plus the reference-derived known-answer
+properties of SURVEY.md §4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import d2r_oracle as O
+from tests.golden.cases import CASES, PARAM_SEED_BASE, INPUT_SEED_BASE, LOSS_SEED
+
+ZERO_GRAD = (".CrossModalAlignment.key.bias", ".att_layer.linears.1.bias", ".crcmc.fc_2.bias")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def digest(t):
+    f = t.detach().double().flatten()
+    idx = torch.linspace(0, f.numel() - 1, 16).long()
+    return torch.cat([f.sum().view(1), f.abs().sum().view(1), f[idx]]).numpy()
+
+
+def check_digest(got, ref, key, rel=2e-4):
+    """digest = [sum, abs-sum, 16 samples]; the plain sum may cancel, so it is judged on the
+    abs-sum's scale, and the samples on the largest sample's scale."""
+    if abs(got[1]) < 1e-5 and abs(ref[1]) < 1e-5:
+        return          # mathematically-zero gradient (e.g. a bias in front of train-mode BN): noise vs noise
+    assert abs(got[1] - ref[1]) <= rel * abs(ref[1]) + 1e-7, key
+    assert abs(got[0] - ref[0]) <= 1e-5 * abs(ref[1]) + 1e-7, key
+    assert np.abs(got[2:] - ref[2:]).max() <= rel * np.abs(ref[2:]).max() + 1e-7, key
+
+
+def run_oracle_case(B, Lt, Li, R, rev, training, realistic, scale, dead_branch=False):
+    P = O.make_params(PARAM_SEED_BASE + R, R, 6, scale)
+    for k, v in P.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    text, image = O.make_inputs(INPUT_SEED_BASE + B, B, Lt, Li, realistic=realistic)
+    text.requires_grad_(True)
+    image.requires_grad_(True)
+    upd = {}
+    out, sim, probs = O.stack_forward(P, text, image, R, 6, rev, training, upd, dead_branch)
+    g = torch.Generator().manual_seed(LOSS_SEED)
+    w_out = torch.randn(out[0].shape, generator=g)
+    w_sim = torch.randn(sim.shape, generator=g)
+    loss = (out[0] * w_out).sum() + (sim * w_sim).sum()
+    loss.backward()
+    return P, text, image, out[0], sim, probs, loss, upd
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_reference_golden(case):
+    name, B, Lt, Li, R, rev, training, realistic, scale = case
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    P, text, image, out, sim, probs, loss, upd = run_oracle_case(B, Lt, Li, R, rev, training, realistic, scale)
+    tol = dict(rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out.detach().numpy(), gold["out"], **tol)
+    np.testing.assert_allclose(sim.detach().numpy(), gold["sim"], **tol)
+    for i, p in enumerate(probs):
+        np.testing.assert_allclose(p.detach().numpy(), gold[f"probs{i}"], rtol=1e-5, atol=1e-7)
+    # gradients pass through softmax(3.6 * q.k): compare on the tensor's own scale
+    for got, ref in ((text.grad.numpy(), gold["d_text"]), (image.grad.numpy(), gold["d_image"])):
+        assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-7
+    dead = set(gold["dead"].tolist())
+    for k, v in P.items():
+        if not v.requires_grad:
+            continue
+        if k in dead:
+            assert v.grad is None and O.is_dead_param(k), k
+        elif k.endswith(ZERO_GRAD):
+            # softmax shift invariance: the key-projection bias gradient is mathematically 0,
+            # both sides hold only rounding noise
+            assert abs(digest(v.grad)[1]) < 1e-3 and abs(gold["gd/" + k][1]) < 1e-3, k
+        else:
+            assert not O.is_dead_param(k), k
+            check_digest(digest(v.grad), gold["gd/" + k], k)
+    for k in gold.files:
+        if k.startswith("buf/"):
+            ref = gold[k]
+            got = upd.get(k[4:], P[k[4:]]).detach().numpy()
+            np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+def test_dead_branch_does_not_change_result():
+    a = run_oracle_case(2, 6, 5, 3, False, True, False, 1.0, dead_branch=False)
+    b = run_oracle_case(2, 6, 5, 3, False, True, False, 1.0, dead_branch=True)
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+
+
+def test_gate_known_answer():
+    """all routers dead (W2=0, b2=-5 -> p=0) => Layer0 outputs == relu(text) exactly,
+    final output finite, sim_paths == 0."""
+    P = O.make_params(1, 3, 6)
+    for k in P:
+        if k.endswith("router.mlp.2.weight"):
+            P[k].zero_()
+        if k.endswith("router.mlp.2.bias"):
+            P[k].fill_(-5.0)
+    text, image = O.make_inputs(3, 2, 6, 4)
+    embs, probs = O.run_cells([text] * 6, image, P, "dynamic_itr_l0", 6, False, None, False)
+    outs, allp = O.aggregate_multi(embs, probs, 6)
+    for o in outs:
+        assert torch.equal(o, torch.relu(text))
+    out, sim, _ = O.stack_forward(P, text, image, 3, 6, False, False)
+    assert torch.isfinite(out[0]).all() and torch.equal(sim, torch.zeros_like(sim))
+
+
+def test_init_known_answer():
+    """fresh init => non-final probs ~ 1/6, final-layer probs ~ tanh(1.5)."""
+    P = O.make_params(5, 3, 6)
+    text, image = O.make_inputs(11, 4, 8, 5)
+    _, _, probs = O.stack_forward(P, text, image, 3, 6, False, False)
+    assert probs[0].shape == (4, 6, 6) and probs[1].shape == (4, 6, 6) and probs[2].shape == (4, 1, 6)
+    assert (probs[0] - 1 / 6).abs().max() < 0.02
+    assert (probs[2] - np.tanh(1.5)).abs().max() < 0.05
+
+
+def test_eval_per_sample_independent():
+    P = O.make_params(5, 3, 6)
+    text, image = O.make_inputs(11, 4, 8, 5)
+    a, _, _ = O.stack_forward(P, text, image, 3, 6, False, False)
+    b, _, _ = O.stack_forward(P, text[:2], image[:2], 3, 6, False, False)
+    np.testing.assert_allclose(a[0][:2].numpy(), b[0].numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("K,R", [(4, 2), (4, 3), (6, 2)])
+def test_reference_derived_shapes(K, R):
+    P = O.make_params(5, R, K)
+    text, image = O.make_inputs(11, 3, 8, 5)
+    out, sim, probs = O.stack_forward(P, text, image, R, K, False, False)
+    assert out[0].shape == (3, 8, 768) and sim.shape == (3, 3)
+    assert sum(p[0].numel() for p in probs) == K * K * (R - 1) + K
