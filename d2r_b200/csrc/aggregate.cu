@@ -1,0 +1,482 @@
+// (c) Aggregation epilogue: probability-weighted sum of the K cell outputs + gated skip.
+// Reference: models/DynamicInteraction.py:50-67 (= :118-132, non-final) and :104-117 (final).
+//
+// HBM-bound.  Fusions that keep per-cell intermediates out of HBM:
+//   * relu() of the RIC cell (Cells.py:36-40) is applied on the fly to the raw layer input;
+//   * GLAC / GESC outputs are [B,D] vectors broadcast over L (Cells.py:173,209): never expanded;
+//   * the mean over L of every output (the next layer's router input, Router.py:23) is produced
+//     in the same pass (forward) and its gradient consumed in the same pass (backward).
+// Grid (D/128, B): a block owns 128 columns of one sample and walks all L rows, so the
+// reductions over L (pooled means, broadcast-cell gradients) need no atomics.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace d2r {
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kCols = 128;   // columns per block (lane owns 4 consecutive)
+
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h[0] = __floats2bfloat162_rn(v[0], v[1]);
+  h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+struct AggP {
+  int K, n_out;
+  long long B, L, D;
+  d2r_ptr8 full, bvec, inputs, out;
+  const float* P;
+  const float* gate;
+  float* pooled;
+  // backward
+  d2r_ptr8 d_out, d_full, d_bvec, d_inputs;
+  const float* d_pooled;
+  float* dP;
+};
+
+// cross-warp sum of per-thread partials v[4] for this block's 128 columns -> lane-owner layout
+// red: [kWarps][kCols]
+__device__ __forceinline__ void block_colsum4(float (&v)[4], float (*red)[kCols], int warp, int lane) {
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = v[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w][lane * 4 + q];
+    v[q] = s;
+  }
+}
+
+// ------------------------------------------------------------------ forward, non-final
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads) agg_fwd_kernel(const AggP p) {
+  __shared__ float sP[K * K];
+  __shared__ float sG[K];
+  __shared__ float red[kWarps][kCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.y;
+  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  if (threadIdx.x < K * K) sP[threadIdx.x] = p.P[b * K * K + threadIdx.x];
+  if (threadIdx.x < K) sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
+  __syncthreads();
+  const bool active = col < p.D;
+  float e[K][4];
+  float pool[K][4];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { e[j][q] = 0.f; pool[j][q] = 0.f; }
+    if (active && p.bvec.p[j]) load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, e[j]);
+  }
+  if (active) {
+    for (long long l = warp; l < p.L; l += kWarps) {
+      const long long off = (b * p.L + l) * p.D + col;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (p.full.p[j]) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[0][q] = fmaxf(e[0][q], 0.f);   // RIC: relu(x)
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a = sG[i] * e[0][q];
+#pragma unroll
+          for (int j = 0; j < K; ++j) a = fmaf(sP[i * K + j], e[j][q], a);
+          v[q] = a;
+          pool[i][q] += a;
+        }
+        store4(static_cast<T*>(const_cast<void*>(p.out.p[i])) + off, v);
+      }
+    }
+  }
+  if (p.pooled) {
+    const float invL = 1.f / (float)p.L;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      block_colsum4(pool[i], red, warp, lane);
+      if (warp == 0 && active) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = pool[i][q] * invL;
+        store4(p.pooled + ((long long)i * p.B + b) * p.D + col, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ forward, final layer
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads) agg_fwd_final_kernel(const AggP p) {
+  __shared__ float sP[K];
+  __shared__ float sG[K];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.y;
+  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  if (threadIdx.x < K) {
+    sP[threadIdx.x] = p.P[b * K + threadIdx.x];
+    sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
+  }
+  __syncthreads();
+  if (col >= p.D) return;
+  float S = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) S += sP[j] + sG[j];
+  const float inv = 1.f / S;
+  float e[K][4];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[j][q] = 0.f;
+    if (p.bvec.p[j]) load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, e[j]);
+  }
+  for (long long l = warp; l < p.L; l += kWarps) {
+    const long long off = (b * p.L + l) * p.D + col;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (p.full.p[j]) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // cell 0: p_0 relu(x_0) + g_0 x_0  (full[0] is the raw layer input ref_wrd[0])
+      float a = sP[0] * fmaxf(e[0][q], 0.f) + sG[0] * e[0][q];
+#pragma unroll
+      for (int j = 1; j < K; ++j) a = fmaf(sP[j], e[j][q], a);
+      v[q] = a;
+    }
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+      if (sG[j] != 0.f) {   // gated skip of cell j's input (rare)
+        float x[4];
+        load4(static_cast<const T*>(p.inputs.p[j]) + off, x);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = fmaf(sG[j], x[q], v[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] *= inv;
+    store4(static_cast<T*>(const_cast<void*>(p.out.p[0])) + off, v);
+  }
+}
+
+// ------------------------------------------------------------------ backward, non-final
+// g_i = d_out_i + d_pooled_i / L.   d_e_j = sum_i P_ij g_i (+ gate_i g_i for j = 0);
+// dP_ij = sum_{l,d} g_i e_j;  d_bvec_j = sum_i P_ij sum_l g_i.
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads) agg_bwd_kernel(const AggP p) {
+  __shared__ float sP[K * K];
+  __shared__ float sG[K];
+  __shared__ float sDpl[K][kCols];
+  __shared__ float red[kWarps][kCols];
+  __shared__ float sdP[kWarps][K * K];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.y;
+  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  const bool active = col < p.D;
+  if (threadIdx.x < K * K) sP[threadIdx.x] = p.P[b * K * K + threadIdx.x];
+  if (threadIdx.x < K) sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
+  const float invL = 1.f / (float)p.L;
+  for (int idx = threadIdx.x; idx < K * kCols; idx += kThreads) {
+    const int i = idx / kCols, c = idx % kCols;
+    const long long gc = (long long)blockIdx.x * kCols + c;
+    sDpl[i][c] = (p.d_pooled && gc < p.D) ? p.d_pooled[((long long)i * p.B + b) * p.D + gc] * invL : 0.f;
+  }
+  __syncthreads();
+  float e[K][4], gsum[K][4], dP[K][K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { e[j][q] = 0.f; gsum[j][q] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < K; ++i) dP[i][j] = 0.f;
+    if (active && p.bvec.p[j]) load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, e[j]);
+  }
+  if (active) {
+    for (long long l = warp; l < p.L; l += kWarps) {
+      const long long off = (b * p.L + l) * p.D + col;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (p.full.p[j]) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
+      float x0pos[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        x0pos[q] = e[0][q] > 0.f ? 1.f : 0.f;
+        e[0][q] = fmaxf(e[0][q], 0.f);
+      }
+      float de[K][4];
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) de[j][q] = 0.f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float g[4];
+        load4(static_cast<const T*>(p.d_out.p[i]) + off, g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          g[q] += sDpl[i][lane * 4 + q];
+          gsum[i][q] += g[q];
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float w = sP[i * K + j] + (j == 0 ? sG[i] : 0.f);
+          float dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            de[j][q] = fmaf(w, g[q], de[j][q]);
+            dot = fmaf(g[q], e[j][q], dot);
+          }
+          dP[i][j] += dot;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (p.full.p[j] && p.d_full.p[j]) {
+          if (j == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) de[0][q] *= x0pos[q];
+          }
+          store4(static_cast<T*>(const_cast<void*>(p.d_full.p[j])) + off, de[j]);
+        }
+      }
+    }
+  }
+  // broadcast-cell gradients: d_bvec_j[b,col] = sum_i P_ij * sum_l g_i
+#pragma unroll
+  for (int i = 0; i < K; ++i) block_colsum4(gsum[i], red, warp, lane);
+  if (warp == 0 && active) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (p.bvec.p[j] && p.d_bvec.p[j]) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < K; ++i) a = fmaf(sP[i * K + j], gsum[i][q], a);
+          v[q] = a;
+        }
+        store4(static_cast<float*>(const_cast<void*>(p.d_bvec.p[j])) + b * p.D + col, v);
+      }
+    }
+  }
+  // dP: warp reduce, then cross-warp via smem, one atomic per (i,j) per block
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float s = warp_sum(dP[i][j]);
+      if (lane == 0) sdP[warp][i * K + j] = s;
+    }
+  __syncthreads();
+  if (threadIdx.x < K * K) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += sdP[w][threadIdx.x];
+    atomicAdd(p.dP + b * K * K + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------ backward, final layer
+// out = N / S,  N = sum_j (p_j e_j + g_j x_j),  S = sum_j (g_j + p_j)
+// dN = d_out / S;  d_e_j = p_j dN;  d_x_j = g_j dN;  dp_j = sum dN.e_j - sum dN.out
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads) agg_bwd_final_kernel(const AggP p) {
+  __shared__ float sP[K];
+  __shared__ float sG[K];
+  __shared__ float red[kWarps][kCols];
+  __shared__ float sdP[kWarps][K + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.y;
+  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  const bool active = col < p.D;
+  if (threadIdx.x < K) {
+    sP[threadIdx.x] = p.P[b * K + threadIdx.x];
+    sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
+  }
+  __syncthreads();
+  float S = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) S += sP[j] + sG[j];
+  const float inv = 1.f / S;
+  float e[K][4], dp[K + 1], dnsum[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dnsum[q] = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    dp[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[j][q] = 0.f;
+    if (active && p.bvec.p[j]) load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, e[j]);
+  }
+  dp[K] = 0.f;   // sum dN . out
+  if (active) {
+    for (long long l = warp; l < p.L; l += kWarps) {
+      const long long off = (b * p.L + l) * p.D + col;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (p.full.p[j]) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
+      float dN[4], N[4], x0[4];
+      load4(static_cast<const T*>(p.d_out.p[0]) + off, dN);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dN[q] *= inv;
+        dnsum[q] += dN[q];
+        x0[q] = e[0][q];
+        e[0][q] = fmaxf(x0[q], 0.f);
+        N[q] = sG[0] * x0[q];
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          N[q] = fmaf(sP[j], e[j][q], N[q]);
+          dot = fmaf(dN[q], e[j][q], dot);
+        }
+        dp[j] += dot;
+      }
+#pragma unroll
+      for (int j = 1; j < K; ++j) {
+        if (sG[j] != 0.f) {
+          float x[4];
+          load4(static_cast<const T*>(p.inputs.p[j]) + off, x);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) N[q] = fmaf(sG[j], x[q], N[q]);
+        }
+      }
+      {
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dot = fmaf(dN[q], N[q] * inv, dot);
+        dp[K] += dot;
+      }
+      // gradients of the full tensors
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (p.full.p[j] && p.d_full.p[j]) {
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            v[q] = j == 0 ? dN[q] * (sP[0] * (x0[q] > 0.f ? 1.f : 0.f) + sG[0]) : sP[j] * dN[q];
+          store4(static_cast<T*>(const_cast<void*>(p.d_full.p[j])) + off, v);
+        }
+        if (j > 0 && p.d_inputs.p[j]) {
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = sG[j] * dN[q];
+          store4(static_cast<T*>(const_cast<void*>(p.d_inputs.p[j])) + off, v);
+        }
+      }
+    }
+  }
+  block_colsum4(dnsum, red, warp, lane);
+  if (warp == 0 && active) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (p.bvec.p[j] && p.d_bvec.p[j]) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = sP[j] * dnsum[q];
+        store4(static_cast<float*>(const_cast<void*>(p.d_bvec.p[j])) + b * p.D + col, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j <= K; ++j) {
+    const float s = warp_sum(dp[j]);
+    if (lane == 0) sdP[warp][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s = 0.f, t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      s += sdP[w][threadIdx.x];
+      t += sdP[w][K];
+    }
+    atomicAdd(p.dP + b * K + threadIdx.x, s - t);
+  }
+}
+
+int fill_common(AggP& q, const d2r_agg_args& a) {
+  D2R_CHECK_ARG(a.K == 4 || a.K == 6, "aggregate: K must be 4 or 6 (got %d)", a.K);
+  D2R_CHECK_ARG(a.final_layer ? a.n_out == 1 : a.n_out == a.K, "aggregate: n_out must be K (or 1 in the final layer)");
+  D2R_CHECK_ARG(a.B > 0 && a.L > 0 && a.D > 0 && a.D % 4 == 0 && a.B <= 65535, "aggregate: bad shape");
+  D2R_CHECK_ARG(a.full.p[0] != nullptr, "aggregate: cell 0 (RIC) needs its raw input in full[0]");
+  for (int j = 0; j < a.K; ++j)
+    D2R_CHECK_ARG((a.full.p[j] != nullptr) != (a.bvec.p[j] != nullptr),
+                  "aggregate: cell %d needs exactly one of full/bvec", j);
+  q.K = a.K; q.n_out = a.n_out; q.B = a.B; q.L = a.L; q.D = a.D;
+  q.full = a.full; q.bvec = a.bvec; q.inputs = a.inputs; q.out = a.out;
+  q.P = a.P; q.gate = a.gate; q.pooled = a.pooled;
+  q.d_pooled = nullptr; q.dP = nullptr;
+  return D2R_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int d2r_aggregate_fwd(const d2r_agg_args* a, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(a != nullptr, "aggregate: null args");
+  AggP q{};
+  if (int rc = fill_common(q, *a)) return rc;
+  dim3 grid((unsigned)((a->D + kCols - 1) / kCols), (unsigned)a->B);
+#define D2R_AGG_LAUNCH(KERN)                                                         \
+  do {                                                                               \
+    if (a->K == 6) { D2R_DISPATCH_DTYPE(a->dtype, T, KERN<T, 6><<<grid, kThreads, 0, st>>>(q)); } \
+    else           { D2R_DISPATCH_DTYPE(a->dtype, T, KERN<T, 4><<<grid, kThreads, 0, st>>>(q)); } \
+  } while (0)
+  if (a->final_layer) D2R_AGG_LAUNCH(agg_fwd_final_kernel);
+  else D2R_AGG_LAUNCH(agg_fwd_kernel);
+  count_launch();
+  return check_launch("agg_fwd_kernel");
+}
+
+int d2r_aggregate_bwd(const d2r_agg_bwd_args* a, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(a != nullptr && a->dP != nullptr, "aggregate_bwd: null args");
+  AggP q{};
+  if (int rc = fill_common(q, a->fwd)) return rc;
+  q.d_out = a->d_out; q.d_full = a->d_full; q.d_bvec = a->d_bvec; q.d_inputs = a->d_inputs;
+  q.d_pooled = a->d_pooled; q.dP = a->dP;
+  const d2r_agg_args* f = &a->fwd;
+  D2R_CUDA_OK(cudaMemsetAsync(a->dP, 0, sizeof(float) * (size_t)f->B * f->n_out * f->K, st));
+  dim3 grid((unsigned)((f->D + kCols - 1) / kCols), (unsigned)f->B);
+#define D2R_AGGB_LAUNCH(KERN)                                                         \
+  do {                                                                                \
+    if (f->K == 6) { D2R_DISPATCH_DTYPE(f->dtype, T, KERN<T, 6><<<grid, kThreads, 0, st>>>(q)); } \
+    else           { D2R_DISPATCH_DTYPE(f->dtype, T, KERN<T, 4><<<grid, kThreads, 0, st>>>(q)); } \
+  } while (0)
+  if (f->final_layer) D2R_AGGB_LAUNCH(agg_bwd_final_kernel);
+  else D2R_AGGB_LAUNCH(agg_bwd_kernel);
+  count_launch();
+  return check_launch("agg_bwd_kernel");
+}
+
+}  // extern "C"
+}  // namespace d2r

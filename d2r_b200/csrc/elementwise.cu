@@ -1,0 +1,495 @@
+// HBM-bound elementwise / row-reduction kernels of the cells: dtype casts, activation
+// backward + bias gradient, row softmax, row L2-norm, FiLM modulation, squared-difference
+// backward, GESC gate.  All use 16-byte vector accesses on the contiguous dimension.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace d2r {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned blocks_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = 148LL * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------ cast / axpby
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  const long long nvec = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+    store8(y + i * 8, v);
+  }
+  for (long long i = nvec * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    Elem<TO>::st(y + i, Elem<TI>::ld(x + i));
+}
+
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ z, float a, float b, T* __restrict__ y,
+                             long long n) {
+  const long long nvec = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float vx[8], vz[8];
+    load8(x + i * 8, vx);
+    if (z) load8(z + i * 8, vz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vx[j] = a * vx[j] + (z ? b * vz[j] : 0.f);
+    store8(y + i * 8, vx);
+  }
+  for (long long i = nvec * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    Elem<T>::st(y + i, a * Elem<T>::ld(x + i) + (z ? b * Elem<T>::ld(z + i) : 0.f));
+}
+
+// ------------------------------------------------------------------ act backward + bias gradient
+// block = 8 warps; a block owns 256 columns x ROWS_PER_BLOCK rows; lane owns 8 consecutive columns.
+constexpr int kRowsPerBlock = 128;
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                                int act, T* __restrict__ dz, float* __restrict__ db,
+                                                                long long rows, int cols, long long ld) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * kRowsPerBlock;
+  const long long r1 = min(rows, r0 + kRowsPerBlock);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col < cols) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      float g[8];
+      load8(dy + r * ld + col, g);
+      if (act != D2R_ACT_NONE) {
+        float yv[8];
+        load8(y + r * ld + col, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          g[j] = act == D2R_ACT_RELU ? (yv[j] > 0.f ? g[j] : 0.f) : g[j] * (1.f - yv[j] * yv[j]);
+      }
+      if (dz) store8(dz + r * ld + col, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+    }
+  }
+  if (db) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    if (blockIdx.x * 256 + c < cols) atomicAdd(db + blockIdx.x * 256 + c, s);
+  }
+}
+
+// ------------------------------------------------------------------ row softmax (one warp per row)
+template <typename TX, typename TY, int PER>
+__global__ void __launch_bounds__(kThreads) softmax_fwd_kernel(const TX* __restrict__ x, long long ldx,
+                                                               TY* __restrict__ y, long long ldy, long long rows,
+                                                               int cols, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TX* xr = x + row * ldx;
+  float v[PER];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < cols ? scale * Elem<TX>::ld(xr + c) : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = (lane + 32 * i) < cols ? __expf(v[i] - mx) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  TY* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    if (c < cols) Elem<TY>::st(yr + c, v[i] * inv);
+  }
+}
+
+template <typename TY, typename TD, typename TX, int PER>
+__global__ void __launch_bounds__(kThreads) softmax_bwd_kernel(const TY* __restrict__ y, long long ldy,
+                                                               const TD* __restrict__ dy, long long lddy,
+                                                               TX* __restrict__ dx, long long lddx, long long rows,
+                                                               int cols, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float yv[PER], gv[PER];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    yv[i] = c < cols ? Elem<TY>::ld(y + row * ldy + c) : 0.f;
+    gv[i] = c < cols ? Elem<TD>::ld(dy + row * lddy + c) : 0.f;
+    dot += yv[i] * gv[i];
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    if (c < cols) Elem<TX>::st(dx + row * lddx + c, scale * yv[i] * (gv[i] - dot));
+  }
+}
+
+// ------------------------------------------------------------------ row L2 norm (one warp per row)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) l2norm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                              float* __restrict__ rnorm, long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * cols;
+  float ss = 0.f;
+  for (int c = lane * 8; c < cols; c += 256) {
+    float v[8];
+    load8(xr + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+  }
+  ss = warp_sum(ss);
+  const float r = 1.f / (sqrtf(ss) + 1e-8f);
+  if (lane == 0) rnorm[row] = r;
+  for (int c = lane * 8; c < cols; c += 256) {
+    float v[8];
+    load8(xr + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= r;
+    store8(y + row * cols + c, v);
+  }
+}
+
+// y = x r, r = 1/(n+eps):  dx = r dy - y (dy.y)/n,  n = 1/r - eps
+template <typename T>
+__global__ void __launch_bounds__(kThreads) l2norm_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy,
+                                                              const float* __restrict__ rnorm, T* __restrict__ dx,
+                                                              long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int c = lane * 8; c < cols; c += 256) {
+    float a[8], b[8];
+    load8(y + row * cols + c, a);
+    load8(dy + row * cols + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot += a[j] * b[j];
+  }
+  dot = warp_sum(dot);
+  const float r = rnorm[row];
+  const float n = fmaxf(1.f / r - 1e-8f, 1e-30f);
+  const float k = dot / n;
+  for (int c = lane * 8; c < cols; c += 256) {
+    float a[8], b[8];
+    load8(y + row * cols + c, a);
+    load8(dy + row * cols + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = r * b[j] - a[j] * k;
+    store8(dx + row * cols + c, b);
+  }
+}
+
+// ------------------------------------------------------------------ FiLM
+template <typename T>
+__global__ void film_fwd_kernel(const T* __restrict__ x, const T* __restrict__ st, T* __restrict__ m,
+                                long long rows, int cols) {
+  const int vpr = cols / 8;
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = (int)(i % vpr) * 8;
+    float xv[8], s[8], t[8];
+    load8(x + r * cols + c, xv);
+    load8(st + r * 2 * cols + c, s);
+    load8(st + r * 2 * cols + cols + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = xv[j] * s[j] + t[j];
+    store8(m + r * cols + c, xv);
+  }
+}
+
+template <typename T>
+__global__ void film_bwd_kernel(const T* __restrict__ dm, const T* __restrict__ x, const T* __restrict__ st,
+                                T* __restrict__ dx, T* __restrict__ dst, long long rows, int cols) {
+  const int vpr = cols / 8;
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = (int)(i % vpr) * 8;
+    float g[8], xv[8], s[8], o[8];
+    load8(dm + r * cols + c, g);
+    load8(x + r * cols + c, xv);
+    load8(st + r * 2 * cols + c, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] * s[j];
+    store8(dx + r * cols + c, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] * xv[j] * (1.f - s[j] * s[j]);   // through tanh
+    store8(dst + r * 2 * cols + c, o);
+    store8(dst + r * 2 * cols + cols + c, g);
+  }
+}
+
+// g = 2 d dsq  (dx = g, dc = -g)
+template <typename T>
+__global__ void sqdiff_bwd_kernel(const T* __restrict__ dsq, const T* __restrict__ d, T* __restrict__ g, long long n) {
+  const long long nvec = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8(dsq + i * 8, a);
+    load8(d + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 2.f * a[j] * b[j];
+    store8(g + i * 8, a);
+  }
+  for (long long i = nvec * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    Elem<T>::st(g + i, 2.f * Elem<T>::ld(dsq + i) * Elem<T>::ld(d + i));
+}
+
+// ------------------------------------------------------------------ GESC gate: block per row
+__device__ __forceinline__ float block_reduce(float v, float* sm, bool is_max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  float r = sm[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, sm[w]) : r + sm[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads) gate_fuse_fwd_kernel(const float* __restrict__ gl,
+                                                                 const float* __restrict__ t,
+                                                                 const float* __restrict__ im, float* __restrict__ g,
+                                                                 float* __restrict__ out, int D) {
+  __shared__ float sm[8];
+  const long long b = blockIdx.x;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < D; c += kThreads) mx = fmaxf(mx, gl[b * D + c]);
+  mx = block_reduce(mx, sm, true);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < D; c += kThreads) sum += __expf(gl[b * D + c] - mx);
+  sum = block_reduce(sum, sm, false);
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < D; c += kThreads) {
+    const float gv = __expf(gl[b * D + c] - mx) * inv;
+    g[b * D + c] = gv;
+    out[b * D + c] = gv * t[b * D + c] + (1.f - gv) * im[b * D + c];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gate_fuse_bwd_kernel(const float* __restrict__ d_out,
+                                                                 const float* __restrict__ g,
+                                                                 const float* __restrict__ t,
+                                                                 const float* __restrict__ im, float* __restrict__ d_gl,
+                                                                 float* __restrict__ d_t, float* __restrict__ d_i, int D) {
+  __shared__ float sm[8];
+  const long long b = blockIdx.x;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < D; c += kThreads) {
+    const long long i = b * D + c;
+    dot += d_out[i] * (t[i] - im[i]) * g[i];
+  }
+  dot = block_reduce(dot, sm, false);
+  for (int c = threadIdx.x; c < D; c += kThreads) {
+    const long long i = b * D + c;
+    const float dg = d_out[i] * (t[i] - im[i]);
+    d_gl[i] = g[i] * (dg - dot);
+    d_t[i] = d_out[i] * g[i];
+    d_i[i] = d_out[i] * (1.f - g[i]);
+  }
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+extern "C" {
+
+int d2r_cast(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) return D2R_OK;
+  D2R_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "cast: pointers must be 16-byte aligned");
+  const unsigned grid = blocks_for(n / 8 + 1, kThreads);
+  if (x_dtype == D2R_F32 && y_dtype == D2R_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, kThreads, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else if (x_dtype == D2R_BF16 && y_dtype == D2R_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+  else if (x_dtype == D2R_F32 && y_dtype == D2R_F32)
+    cast_kernel<float, float><<<grid, kThreads, 0, st>>>((const float*)x, (float*)y, n);
+  else if (x_dtype == D2R_BF16 && y_dtype == D2R_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+  else
+    return set_error(D2R_ERR_ARG, "cast: bad dtypes %d -> %d", x_dtype, y_dtype);
+  count_launch();
+  return check_launch("cast_kernel");
+}
+
+int d2r_axpby(const void* x, const void* z, int32_t dtype, float a, float b, void* y, int64_t n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) return D2R_OK;
+  const unsigned grid = blocks_for(n / 8 + 1, kThreads);
+  D2R_DISPATCH_DTYPE(dtype, T, axpby_kernel<T><<<grid, kThreads, 0, st>>>((const T*)x, (const T*)z, a, b, (T*)y, n));
+  count_launch();
+  return check_launch("axpby_kernel");
+}
+
+int d2r_bias_act_bwd(const void* dy, const void* y, int32_t dtype, int32_t act, void* dz, float* db, int64_t rows,
+                     int32_t cols, int64_t ld, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols % 8 == 0 && ld % 8 == 0, "bias_act_bwd: cols/ld must be multiples of 8");
+  D2R_CHECK_ARG(act == D2R_ACT_NONE || y != nullptr, "bias_act_bwd: activation needs y");
+  if (rows <= 0) return D2R_OK;
+  dim3 grid((cols + 255) / 256, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)y, act,
+                                                                                (T*)dz, db, rows, cols, ld));
+  count_launch();
+  return check_launch("bias_act_bwd_kernel");
+}
+
+#define D2R_SOFTMAX_FWD(TX, TY)                                                                              \
+  do {                                                                                                       \
+    if (cols <= 64)                                                                                          \
+      softmax_fwd_kernel<TX, TY, 2><<<grid, kThreads, 0, st>>>((const TX*)x, ldx, (TY*)y, ldy, rows, cols, scale); \
+    else if (cols <= 256)                                                                                    \
+      softmax_fwd_kernel<TX, TY, 8><<<grid, kThreads, 0, st>>>((const TX*)x, ldx, (TY*)y, ldy, rows, cols, scale); \
+    else                                                                                                     \
+      softmax_fwd_kernel<TX, TY, 32><<<grid, kThreads, 0, st>>>((const TX*)x, ldx, (TY*)y, ldy, rows, cols, scale); \
+  } while (0)
+
+int d2r_softmax_fwd(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy, int64_t rows,
+                    int32_t cols, float scale, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols >= 1 && cols <= 1024, "softmax: cols %d outside [1,1024]", cols);
+  if (rows <= 0) return D2R_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (x_dtype == D2R_F32 && y_dtype == D2R_BF16) D2R_SOFTMAX_FWD(float, __nv_bfloat16);
+  else if (x_dtype == D2R_F32 && y_dtype == D2R_F32) D2R_SOFTMAX_FWD(float, float);
+  else if (x_dtype == D2R_BF16 && y_dtype == D2R_BF16) D2R_SOFTMAX_FWD(__nv_bfloat16, __nv_bfloat16);
+  else return set_error(D2R_ERR_ARG, "softmax_fwd: unsupported dtypes %d -> %d", x_dtype, y_dtype);
+  count_launch();
+  return check_launch("softmax_fwd_kernel");
+}
+
+#define D2R_SOFTMAX_BWD(TY, TD, TX)                                                                    \
+  do {                                                                                                 \
+    if (cols <= 64)                                                                                    \
+      softmax_bwd_kernel<TY, TD, TX, 2><<<grid, kThreads, 0, st>>>((const TY*)y, ldy, (const TD*)dy, lddy, \
+                                                                   (TX*)dx, lddx, rows, cols, scale);  \
+    else if (cols <= 256)                                                                              \
+      softmax_bwd_kernel<TY, TD, TX, 8><<<grid, kThreads, 0, st>>>((const TY*)y, ldy, (const TD*)dy, lddy, \
+                                                                   (TX*)dx, lddx, rows, cols, scale);  \
+    else                                                                                               \
+      softmax_bwd_kernel<TY, TD, TX, 32><<<grid, kThreads, 0, st>>>((const TY*)y, ldy, (const TD*)dy, lddy, \
+                                                                    (TX*)dx, lddx, rows, cols, scale); \
+  } while (0)
+
+int d2r_softmax_bwd(const void* y, int32_t y_dtype, int64_t ldy, const void* dy, int32_t dy_dtype, int64_t lddy,
+                    void* dx, int32_t dx_dtype, int64_t lddx, int64_t rows, int32_t cols, float scale, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols >= 1 && cols <= 1024, "softmax: cols %d outside [1,1024]", cols);
+  if (rows <= 0) return D2R_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (y_dtype == D2R_BF16 && dy_dtype == D2R_F32 && dx_dtype == D2R_BF16)
+    D2R_SOFTMAX_BWD(__nv_bfloat16, float, __nv_bfloat16);
+  else if (y_dtype == D2R_F32 && dy_dtype == D2R_F32 && dx_dtype == D2R_F32)
+    D2R_SOFTMAX_BWD(float, float, float);
+  else if (y_dtype == D2R_BF16 && dy_dtype == D2R_BF16 && dx_dtype == D2R_BF16)
+    D2R_SOFTMAX_BWD(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+  else
+    return set_error(D2R_ERR_ARG, "softmax_bwd: unsupported dtypes y=%d dy=%d dx=%d", y_dtype, dy_dtype, dx_dtype);
+  count_launch();
+  return check_launch("softmax_bwd_kernel");
+}
+
+int d2r_l2norm_fwd(const void* x, int32_t dtype, void* y, float* rnorm, int64_t rows, int32_t cols, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols % 8 == 0, "l2norm: cols must be a multiple of 8");
+  if (rows <= 0) return D2R_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  D2R_DISPATCH_DTYPE(dtype, T, l2norm_fwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)x, (T*)y, rnorm, rows, cols));
+  count_launch();
+  return check_launch("l2norm_fwd_kernel");
+}
+
+int d2r_l2norm_bwd(const void* y, const void* dy, int32_t dtype, const float* rnorm, void* dx, int64_t rows,
+                   int32_t cols, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols % 8 == 0, "l2norm: cols must be a multiple of 8");
+  if (rows <= 0) return D2R_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  D2R_DISPATCH_DTYPE(dtype, T,
+                     l2norm_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)y, (const T*)dy, rnorm, (T*)dx, rows, cols));
+  count_launch();
+  return check_launch("l2norm_bwd_kernel");
+}
+
+int d2r_film_fwd(const void* x, const void* st_, int32_t dtype, void* m, int64_t rows, int32_t cols, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols % 8 == 0, "film: cols must be a multiple of 8");
+  if (rows <= 0) return D2R_OK;
+  const unsigned grid = blocks_for(rows * (cols / 8), kThreads);
+  D2R_DISPATCH_DTYPE(dtype, T, film_fwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)x, (const T*)st_, (T*)m, rows, cols));
+  count_launch();
+  return check_launch("film_fwd_kernel");
+}
+
+int d2r_film_bwd(const void* dm, const void* x, const void* st_, int32_t dtype, void* dx, void* d_st, int64_t rows,
+                 int32_t cols, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(cols % 8 == 0, "film: cols must be a multiple of 8");
+  if (rows <= 0) return D2R_OK;
+  const unsigned grid = blocks_for(rows * (cols / 8), kThreads);
+  D2R_DISPATCH_DTYPE(dtype, T,
+                     film_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dm, (const T*)x, (const T*)st_, (T*)dx,
+                                                                  (T*)d_st, rows, cols));
+  count_launch();
+  return check_launch("film_bwd_kernel");
+}
+
+int d2r_sqdiff_bwd(const void* dsq, const void* d, int32_t dtype, void* g, int64_t n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) return D2R_OK;
+  const unsigned grid = blocks_for(n / 8 + 1, kThreads);
+  D2R_DISPATCH_DTYPE(dtype, T, sqdiff_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dsq, (const T*)d, (T*)g, n));
+  count_launch();
+  return check_launch("sqdiff_bwd_kernel");
+}
+
+int d2r_gate_fuse_fwd(const float* gl, const float* t, const float* i, float* g, float* out, int64_t B, int32_t D,
+                      void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (B <= 0) return D2R_OK;
+  gate_fuse_fwd_kernel<<<(unsigned)B, kThreads, 0, st>>>(gl, t, i, g, out, D);
+  count_launch();
+  return check_launch("gate_fuse_fwd_kernel");
+}
+
+int d2r_gate_fuse_bwd(const float* d_out, const float* g, const float* t, const float* i, float* d_gl, float* d_t,
+                      float* d_i, int64_t B, int32_t D, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (B <= 0) return D2R_OK;
+  gate_fuse_bwd_kernel<<<(unsigned)B, kThreads, 0, st>>>(d_out, g, t, i, d_gl, d_t, d_i, D);
+  count_launch();
+  return check_launch("gate_fuse_bwd_kernel");
+}
+
+}  // extern "C"
+}  // namespace d2r

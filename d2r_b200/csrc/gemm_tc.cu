@@ -1,0 +1,437 @@
+// tcgen05 / TMEM / TMA batched GEMM with fused epilogue (bf16 operands, fp32 accumulation).
+//
+//   C[z] = epilogue(alpha * A[z] (m x k) * B[z]^T (n x k))
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor.4d -> 128B-swizzled smem ring)
+//   warp 1      MMA issuer     (one thread: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> bias/act/residual -> global)
+// Accumulators are double-buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i
+// overlaps the main loop of tile i+1.  Operands may be K-major or MN-major (transposed) so the
+// same kernel serves forward (x W^T), data-gradient (dy W) and weight-gradient (dy^T x).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace d2r {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int ATOM_BYTES = 64 * BK * 2;   // one [64 x 64] bf16 swizzle tile = 8 KB
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+struct TcParams {
+  int m, n, k;
+  int batch_inner;
+  int m_tiles, n_tiles, k_blocks, split_k, kb_per_split;
+  long long num_tiles;
+  int a_bcast_i, a_bcast_o, b_bcast_i, b_bcast_o;   // 1: batch stride 0 -> coordinate pinned to 0
+  void* c;
+  void* c2;
+  const float* bias;
+  const void* residual;
+  long long ldc, ldr, c_so, c_si, r_so, r_si, bias_sz;
+  float alpha;
+  int act, epilogue, c_dtype, r_dtype, atomic;
+};
+
+struct TileCoord {
+  int m0, n0, zi, zo, z, kb0, kb1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long t, int bn) {
+  TileCoord tc;
+  int nb = static_cast<int>(t % p.n_tiles);
+  t /= p.n_tiles;
+  int ks = static_cast<int>(t % p.split_k);
+  t /= p.split_k;
+  int mb = static_cast<int>(t % p.m_tiles);
+  int z = static_cast<int>(t / p.m_tiles);
+  tc.m0 = mb * BM;
+  tc.n0 = nb * bn;
+  tc.z = z;
+  tc.zi = z % p.batch_inner;
+  tc.zo = z / p.batch_inner;
+  tc.kb0 = ks * p.kb_per_split;
+  tc.kb1 = min(p.k_blocks, tc.kb0 + p.kb_per_split);
+  return tc;
+}
+
+template <typename TC>
+__device__ __forceinline__ void store_group(TC* cptr, const float (&v)[8], int nvalid, bool atomic) {
+  if (atomic) {
+    if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nvalid) atomicAdd(reinterpret_cast<float*>(cptr) + i, v[i]);
+    }
+    return;
+  }
+  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(cptr) & 15) == 0) {
+    store8(cptr, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nvalid) Elem<TC>::st(cptr + i, v[i]);
+  }
+}
+
+template <typename TR>
+__device__ __forceinline__ void load_group(const TR* rptr, float (&v)[8], int nvalid) {
+  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(rptr) & 15) == 0) {
+    load8(rptr, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (i < nvalid) ? Elem<TR>::ld(rptr + i) : 0.f;
+  }
+}
+
+// one thread: 32 consecutive accumulator columns of one output row
+__device__ __forceinline__ void epilogue_row(const TcParams& p, const uint32_t (&r)[32], long long row, int col0,
+                                             const TileCoord& tc) {
+  const long long c_off = static_cast<long long>(tc.zo) * p.c_so + static_cast<long long>(tc.zi) * p.c_si +
+                          row * p.ldc;
+  const long long r_off = static_cast<long long>(tc.zo) * p.r_so + static_cast<long long>(tc.zi) * p.r_si +
+                          row * p.ldr;
+  const float* bias = p.bias ? p.bias + static_cast<long long>(tc.z) * p.bias_sz : nullptr;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col >= p.n) break;
+    const int nvalid = min(8, p.n - col);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(r[g * 8 + i]);
+    if (bias) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nvalid) v[i] += __ldg(bias + col + i);
+    }
+    float res[8];
+    if (p.residual) {
+      if (p.r_dtype == D2R_BF16)
+        load_group(reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col, res, nvalid);
+      else
+        load_group(reinterpret_cast<const float*>(p.residual) + r_off + col, res, nvalid);
+    }
+    if (p.epilogue == D2R_EPI_SQDIFF) {
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        d[i] = res[i] - v[i];
+        v[i] = d[i] * d[i];
+      }
+      if (p.c_dtype == D2R_BF16)
+        store_group(reinterpret_cast<__nv_bfloat16*>(p.c2) + c_off + col, d, nvalid, false);
+      else
+        store_group(reinterpret_cast<float*>(p.c2) + c_off + col, d, nvalid, false);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
+      if (p.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += res[i];
+      }
+    }
+    if (p.c_dtype == D2R_BF16)
+      store_group(reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + col, v, nvalid, false);
+    else
+      store_group(reinterpret_cast<float*>(p.c) + c_off + col, v, nvalid, p.atomic != 0);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles must start on a 1024-byte boundary
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, BN);
+        const int azi = p.a_bcast_i ? 0 : tc.zi, azo = p.a_bcast_o ? 0 : tc.zo;
+        const int bzi = p.b_bcast_i ? 0 : tc.zi, bzo = p.b_bcast_o ? 0 : tc.zo;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_4d(sa, &tmA, &full_bar[stage], kb * BK, tc.m0, azi, azo);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_4d(sa + i * ATOM_BYTES, &tmA, &full_bar[stage], tc.m0 + 64 * i, kb * BK, azi, azo);
+          }
+          if constexpr (!B_MN) {
+            tma_load_4d(sb, &tmB, &full_bar[stage], kb * BK, tc.n0, bzi, bzo);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_4d(sb + i * ATOM_BYTES, &tmB, &full_bar[stage], tc.n0 + 64 * i, kb * BK, bzi, bzo);
+          }
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, BN);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 8-row groups are 1024 B apart (SBO), a K step of 16 elements is 32 B.
+            // MN-major: 64-wide MN tiles are 8 KB apart (LBO), 8-deep K groups 1024 B apart (SBO),
+            //           a K step of 16 is two K groups = 2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, ATOM_BYTES, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, ATOM_BYTES, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- epilogue (4 warps)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t, BN);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = tc.m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tc.n0 + c * 32;
+        if (col0 >= p.n) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + static_cast<uint32_t>(acc * BN + c * 32) + (static_cast<uint32_t>(q * 32) << 16), r);
+        tmem_ld_wait();
+        if (row < p.m) epilogue_row(p, r, row, col0, tc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(f);
+    tried = true;
+  }
+  return fn;
+}
+
+// 4-D map {inner (contiguous), rows, batch_inner, batch_outer}; bf16; 128-byte swizzle; OOB -> 0
+int encode_operand(CUtensorMap* tm, const void* base, long long inner, long long rows, long long bi, long long bo,
+                   long long ld, long long si, long long so, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(D2R_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const long long row_bytes = ld * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)bi, (cuuint64_t)bo};
+  cuuint64_t strides[3] = {(cuuint64_t)row_bytes, (cuuint64_t)(bi > 1 ? si * 2 : row_bytes),
+                           (cuuint64_t)(bo > 1 ? so * 2 : row_bytes)};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(D2R_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d): dims=[%lld,%lld,%lld,%lld] ld=%lld si=%lld so=%lld", (int)r,
+                     inner, rows, bi, bo, ld, si, so);
+  return D2R_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  long long grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<(unsigned)grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  count_launch();
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int BN>
+int launch_tc_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
+                    cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(tmA, tmB, p, stream);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true>(tmA, tmB, p, stream);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false>(tmA, tmB, p, stream);
+  return launch_tc<BN, true, true>(tmA, tmB, p, stream);
+}
+
+}  // namespace
+
+int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
+  D2R_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0 && a.batch > 0 && a.batch_inner > 0, "gemm: empty problem");
+  D2R_CHECK_ARG(a.batch % a.batch_inner == 0, "gemm: batch %d not a multiple of batch_inner %d", a.batch,
+                a.batch_inner);
+  D2R_CHECK_ARG((reinterpret_cast<uintptr_t>(a.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.b) & 15) == 0,
+                "gemm(bf16): A and B must be 16-byte aligned");
+  D2R_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0 && a.a_so % 8 == 0 && a.a_si % 8 == 0 && a.b_so % 8 == 0 &&
+                    a.b_si % 8 == 0,
+                "gemm(bf16): lda/ldb/batch strides must be multiples of 8 elements (TMA 16-byte rule)");
+  D2R_CHECK_ARG(a.epilogue == D2R_EPI_STD || (a.residual && a.c2), "gemm: SQDIFF needs residual and c2");
+  const int bo = a.batch / a.batch_inner, bi = a.batch_inner;
+  int split_k = a.split_k > 1 ? a.split_k : 1;
+
+  int bn = a.tile_n;
+  if (bn == 0) bn = a.n <= 64 ? 64 : (a.n <= 128 ? 128 : 256);
+  D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "gemm: tile_n %d unsupported", bn);
+
+  TcParams p;
+  p.m = a.m; p.n = a.n; p.k = a.k;
+  p.batch_inner = bi;
+  p.m_tiles = (a.m + BM - 1) / BM;
+  p.n_tiles = (a.n + bn - 1) / bn;
+  p.k_blocks = (a.k + BK - 1) / BK;
+  if (split_k > p.k_blocks) split_k = p.k_blocks;
+  p.kb_per_split = (p.k_blocks + split_k - 1) / split_k;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.num_tiles = 1LL * p.m_tiles * p.n_tiles * p.split_k * a.batch;
+  const bool atomic = a.accumulate || p.split_k > 1;
+  D2R_CHECK_ARG(!atomic || a.c_dtype == D2R_F32, "gemm: accumulate/split_k need an fp32 C");
+  D2R_CHECK_ARG(!atomic || (a.epilogue == D2R_EPI_STD && a.act == D2R_ACT_NONE && !a.residual),
+                "gemm: accumulate/split_k support only the plain epilogue");
+  p.a_bcast_i = (bi > 1 && a.a_si == 0); p.a_bcast_o = (bo > 1 && a.a_so == 0);
+  p.b_bcast_i = (bi > 1 && a.b_si == 0); p.b_bcast_o = (bo > 1 && a.b_so == 0);
+  p.c = a.c; p.c2 = a.c2; p.bias = a.bias; p.residual = a.residual;
+  p.ldc = a.ldc; p.ldr = a.ldr; p.c_so = a.c_so; p.c_si = a.c_si; p.r_so = a.r_so; p.r_si = a.r_si;
+  p.bias_sz = a.bias_sz;
+  p.alpha = a.alpha; p.act = a.act; p.epilogue = a.epilogue; p.c_dtype = a.c_dtype; p.r_dtype = a.r_dtype;
+  p.atomic = atomic ? 1 : 0;
+
+  if (p.split_k > 1 && !a.accumulate) {
+    // split-K partial sums are combined with atomics: C must start at zero (dense C only)
+    D2R_CHECK_ARG(a.batch == 1 && a.ldc == a.n, "gemm: split_k without accumulate needs a dense, unbatched C");
+    D2R_CUDA_OK(cudaMemsetAsync(a.c, 0, sizeof(float) * (size_t)a.m * a.n, stream));
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand: inner = k, rows = m|n, box rows = tile rows.  MN-major: inner = m|n, rows = k, box rows = BK.
+  const long long a_bi = p.a_bcast_i ? 1 : bi, a_bo = p.a_bcast_o ? 1 : bo;
+  const long long b_bi = p.b_bcast_i ? 1 : bi, b_bo = p.b_bcast_o ? 1 : bo;
+  if (!a.a_mn_major) rc = encode_operand(&tmA, a.a, a.k, a.m, a_bi, a_bo, a.lda, a.a_si, a.a_so, BM);
+  else               rc = encode_operand(&tmA, a.a, a.m, a.k, a_bi, a_bo, a.lda, a.a_si, a.a_so, BK);
+  if (rc) return rc;
+  if (!a.b_mn_major) rc = encode_operand(&tmB, a.b, a.k, a.n, b_bi, b_bo, a.ldb, a.b_si, a.b_so, bn);
+  else               rc = encode_operand(&tmB, a.b, a.n, a.k, b_bi, b_bo, a.ldb, a.b_si, a.b_so, BK);
+  if (rc) return rc;
+
+  const bool amn = a.a_mn_major != 0, bmn = a.b_mn_major != 0;
+  if (bn == 64) return launch_tc_major<64>(amn, bmn, tmA, tmB, p, stream);
+  if (bn == 128) return launch_tc_major<128>(amn, bmn, tmA, tmB, p, stream);
+  return launch_tc_major<256>(amn, bmn, tmA, tmB, p, stream);
+}
+
+}  // namespace d2r
