@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
         ("batch", C.c_int32), ("batch_inner", C.c_int32),
         ("act", C.c_int32), ("epilogue", C.c_int32), ("r_dtype", C.c_int32),
         ("accumulate", C.c_int32), ("split_k", C.c_int32),
-        ("alpha", C.c_float), ("tile_n", C.c_int32),
+        ("alpha", C.c_float), ("tile_n", C.c_int32), ("act_cols", C.c_int32), ("reserved0", C.c_int32),
         ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("c2", C.c_void_p),
         ("bias", C.c_void_p), ("residual", C.c_void_p),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64), ("ldr", C.c_int64),
@@ -99,9 +99,10 @@ SYMBOLS = {
     "d2r_l2norm_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "d2r_l2norm_bwd": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "d2r_film_fwd": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp]),
-    "d2r_film_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "d2r_film_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "d2r_axpby": (C.c_int, [_vp, _vp, _i32, _f, _f, _vp, _i64, _vp]),
-    "d2r_sqdiff_bwd": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp]),
+    "d2r_sqdiff_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "d2r_mul": (C.c_int, [_vp, _vp, _i32, _f, _vp, _i64, _vp]),
     "d2r_saf_fwd": (C.c_int, [C.POINTER(SafArgs), _vp]),
     "d2r_saf_bwd": (C.c_int, [C.POINTER(SafBwdArgs), _vp]),
     "d2r_gate_fuse_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),

@@ -227,7 +227,7 @@ __global__ void film_fwd_kernel(const T* __restrict__ x, const T* __restrict__ s
 
 template <typename T>
 __global__ void film_bwd_kernel(const T* __restrict__ dm, const T* __restrict__ x, const T* __restrict__ st,
-                                T* __restrict__ dx, T* __restrict__ dst, long long rows, int cols) {
+                                const T* __restrict__ add, T* __restrict__ dx, T* __restrict__ dst, long long rows, int cols) {
   const int vpr = cols / 8;
   const long long total = rows * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -239,6 +239,12 @@ __global__ void film_bwd_kernel(const T* __restrict__ dm, const T* __restrict__ 
     load8(st + r * 2 * cols + c, s);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = g[j] * s[j];
+    if (add) {
+      float ad[8];
+      load8(add + r * cols + c, ad);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += ad[j];
+    }
     store8(dx + r * cols + c, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = g[j] * xv[j] * (1.f - s[j] * s[j]);   // through tanh
@@ -249,7 +255,8 @@ __global__ void film_bwd_kernel(const T* __restrict__ dm, const T* __restrict__ 
 
 // g = 2 d dsq  (dx = g, dc = -g)
 template <typename T>
-__global__ void sqdiff_bwd_kernel(const T* __restrict__ dsq, const T* __restrict__ d, T* __restrict__ g, long long n) {
+__global__ void sqdiff_bwd_kernel(const T* __restrict__ dsq, const T* __restrict__ d, const T* __restrict__ add,
+                                  T* __restrict__ g, T* __restrict__ gx, long long n) {
   const long long nvec = n / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
@@ -258,10 +265,28 @@ __global__ void sqdiff_bwd_kernel(const T* __restrict__ dsq, const T* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = 2.f * a[j] * b[j];
     store8(g + i * 8, a);
+    if (gx) {
+      if (add) {
+        load8(add + i * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += b[j];
+      }
+      store8(gx + i * 8, a);
+    }
   }
   for (long long i = nvec * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
-    Elem<T>::st(g + i, 2.f * Elem<T>::ld(dsq + i) * Elem<T>::ld(d + i));
+  {
+    const float v = 2.f * Elem<T>::ld(dsq + i) * Elem<T>::ld(d + i);
+    Elem<T>::st(g + i, v);
+    if (gx) Elem<T>::st(gx + i, v + (add ? Elem<T>::ld(add + i) : 0.f));
+  }
+}
+
+template <typename T>
+__global__ void mul_kernel(const T* __restrict__ x, const T* __restrict__ z, float alpha, T* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    Elem<T>::st(y + i, alpha * Elem<T>::ld(x + i) * Elem<T>::ld(z + i));
 }
 
 // ------------------------------------------------------------------ GESC gate: block per row
@@ -451,24 +476,34 @@ int d2r_film_fwd(const void* x, const void* st_, int32_t dtype, void* m, int64_t
   return check_launch("film_fwd_kernel");
 }
 
-int d2r_film_bwd(const void* dm, const void* x, const void* st_, int32_t dtype, void* dx, void* d_st, int64_t rows,
-                 int32_t cols, void* stream) {
+int d2r_film_bwd(const void* dm, const void* x, const void* st_, const void* add, int32_t dtype, void* dx, void* d_st,
+                 int64_t rows, int32_t cols, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   D2R_CHECK_ARG(cols % 8 == 0, "film: cols must be a multiple of 8");
   if (rows <= 0) return D2R_OK;
   const unsigned grid = blocks_for(rows * (cols / 8), kThreads);
   D2R_DISPATCH_DTYPE(dtype, T,
-                     film_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dm, (const T*)x, (const T*)st_, (T*)dx,
+                     film_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dm, (const T*)x, (const T*)st_, (const T*)add, (T*)dx,
                                                                   (T*)d_st, rows, cols));
   count_launch();
   return check_launch("film_bwd_kernel");
 }
 
-int d2r_sqdiff_bwd(const void* dsq, const void* d, int32_t dtype, void* g, int64_t n, void* stream) {
+int d2r_mul(const void* x, const void* z, int32_t dtype, float alpha, void* y, int64_t n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) return D2R_OK;
+  const unsigned grid = blocks_for(n, kThreads);
+  D2R_DISPATCH_DTYPE(dtype, T, mul_kernel<T><<<grid, kThreads, 0, st>>>((const T*)x, (const T*)z, alpha, (T*)y, n));
+  count_launch();
+  return check_launch("mul_kernel");
+}
+
+int d2r_sqdiff_bwd(const void* dsq, const void* d, const void* add, int32_t dtype, void* g, void* gx, int64_t n,
+                   void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   if (n <= 0) return D2R_OK;
   const unsigned grid = blocks_for(n / 8 + 1, kThreads);
-  D2R_DISPATCH_DTYPE(dtype, T, sqdiff_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dsq, (const T*)d, (T*)g, n));
+  D2R_DISPATCH_DTYPE(dtype, T, sqdiff_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dsq, (const T*)d, (const T*)add, (T*)g, (T*)gx, n));
   count_launch();
   return check_launch("sqdiff_bwd_kernel");
 }

@@ -23,7 +23,7 @@ struct SimtParams {
   long long lda, ldb, ldc, ldr;
   long long a_so, a_si, b_so, b_si, c_so, c_si, r_so, r_si, bias_sz;
   float alpha;
-  int act, epilogue, c_dtype, r_dtype, atomic;
+  int act, epilogue, c_dtype, r_dtype, atomic, act_cols;
   int split_k, k_per_split;
 };
 
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
         else reinterpret_cast<float*>(p.c2)[c_off + col] = d;
         v = d * d;
       } else {
-        v = apply_act(v, p.act) + res;
+        if (p.act_cols == 0 || col < p.act_cols) v = apply_act(v, p.act);
+        v += res;
       }
       if (p.c_dtype == D2R_BF16) reinterpret_cast<__nv_bfloat16*>(p.c)[c_off + col] = __float2bfloat16_rn(v);
       else if (p.atomic) atomicAdd(reinterpret_cast<float*>(p.c) + c_off + col, v);
@@ -139,6 +140,7 @@ int gemm_simt(const d2r_gemm_args& a, cudaStream_t stream) {
   D2R_CHECK_ARG(!atomic || (a.epilogue == D2R_EPI_STD && a.act == D2R_ACT_NONE && !a.residual),
                 "gemm: accumulate/split_k support only the plain epilogue");
   p.atomic = atomic ? 1 : 0;
+  p.act_cols = a.act_cols;
   if (p.split_k > 1 && !a.accumulate) {
     D2R_CHECK_ARG(a.batch == 1 && a.ldc == a.n, "gemm: split_k without accumulate needs a dense, unbatched C");
     D2R_CUDA_OK(cudaMemsetAsync(a.c, 0, sizeof(float) * (size_t)a.m * a.n, stream));

@@ -46,7 +46,7 @@ struct TcParams {
   const void* residual;
   long long ldc, ldr, c_so, c_si, r_so, r_si, bias_sz;
   float alpha;
-  int act, epilogue, c_dtype, r_dtype, atomic;
+  int act, epilogue, c_dtype, r_dtype, atomic, act_cols;
 };
 
 struct TileCoord {
@@ -141,7 +141,10 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const uint32_t (
         store_group(reinterpret_cast<float*>(p.c2) + c_off + col, d, nvalid, false);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
+      if (p.act_cols == 0 || col < p.act_cols) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
+      }
       if (p.residual) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += res[i];
@@ -409,6 +412,8 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   p.bias_sz = a.bias_sz;
   p.alpha = a.alpha; p.act = a.act; p.epilogue = a.epilogue; p.c_dtype = a.c_dtype; p.r_dtype = a.r_dtype;
   p.atomic = atomic ? 1 : 0;
+  p.act_cols = a.act_cols;
+  D2R_CHECK_ARG(a.act_cols % 8 == 0, "gemm: act_cols must be a multiple of 8");
 
   if (p.split_k > 1 && !a.accumulate) {
     // split-K partial sums are combined with atomics: C must start at zero (dense C only)

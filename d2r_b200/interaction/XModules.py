@@ -1,0 +1,113 @@
+"""Mirror of the live parts of reference models/XModules.py: l1norm/l2norm :14-24, CrossModalAlignment
+:277-328 (live part :300-310; the reverse-attention / ContrastiveLoss branch :312-326 is dead work whose
+result every caller discards -- its parameters fc_1/fc_2 are kept for state_dict parity, the returned
+loss is a constant 0), AttentionFiltration :366-394.  ``js_div`` and ``Block`` (used by the backbone
+after the stack) stay plain PyTorch."""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import stack as S
+from .. import kernels as K
+from ..autograd import run_block
+
+
+def l2norm(X, dim=-1, eps=1e-8):
+    norm = torch.pow(X, 2).sum(dim=dim, keepdim=True).sqrt() + eps
+    return torch.div(X, norm)
+
+
+def l1norm(X, dim, eps=1e-8):
+    norm = torch.abs(X).sum(dim=dim, keepdim=True) + eps
+    return torch.div(X, norm)
+
+
+def js_div(p_output, q_output, get_softmax=True):
+    """reference models/XModules.py:32-41 (post-stack loss term; plain PyTorch)."""
+    kl = nn.KLDivLoss(reduction='batchmean')
+    if get_softmax:
+        p_output = F.softmax(p_output, dim=-1)
+        q_output = F.softmax(q_output, dim=-1)
+    log_mean_output = ((p_output + q_output) / 2).log()
+    return (kl(log_mean_output, p_output) + kl(log_mean_output, q_output)) / 2
+
+
+def hidden_size_of(config) -> int:
+    return int(getattr(config, "hidden_size", 768))
+
+
+def _cma_block(module, text_emb, image_emb):
+    def fwd(env, xs):
+        x, z = xs
+        kv = S._KV(env, z, ["C"])
+        out, sv = S._cma_fwd(env, "C", x, kv, 0)
+        return (out,), dict(cma=sv, kv=kv, x=x)
+
+    def bwd(env, st, grads):
+        dx = S._cma_bwd(env, "C", st["x"], st["kv"], 0, st["cma"], grads[0], 1.0, None)
+        dz = st["kv"].backward(env, None)
+        return dx, dz
+
+    return run_block(module, [text_emb, image_emb], fwd, bwd, prefix="C.")[0]
+
+
+class CrossModalAlignment(nn.Module):
+    def __init__(self, config, args):
+        super(CrossModalAlignment, self).__init__()
+        self.config, self.args = config, args
+        hs = hidden_size_of(config)
+        self.query = nn.Linear(hs, hs)
+        self.key = nn.Linear(hs, hs)
+        self.value = nn.Linear(hs, hs)
+        self.fc_1 = nn.Linear(hs, hs)   # dead in the reference, kept for state_dict parity
+        self.fc_2 = nn.Linear(hs, hs)
+
+    def forward(self, text_emb, image_emb):
+        out = _cma_block(self, text_emb, image_emb)
+        return out, out.new_zeros(())   # (text_img_rep_init, text_img_loss); the loss is discarded upstream
+
+
+class AttentionFiltration(nn.Module):
+    def __init__(self, sim_dim):
+        super(AttentionFiltration, self).__init__()
+        self.attn_sim_w = nn.Linear(sim_dim, 1)
+        self.bn = nn.BatchNorm1d(1)
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.children():
+            if isinstance(m, nn.Linear):
+                r = np.sqrt(6.) / np.sqrt(m.in_features + m.out_features)
+                m.weight.data.uniform_(-r, r)
+                m.bias.data.fill_(0)
+            elif isinstance(m, nn.BatchNorm1d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def forward(self, sim_emb):
+        """sim_emb (B, L+1, D) -> (B, D)."""
+        def fwd(env, xs):
+            s = xs[0]
+            P = env.P
+            sg, sl = s[:, 0].contiguous(), s[:, 1:].contiguous()
+            out, saved = K.saf_fwd(sg, sl, P["attn_sim_w.weight"].detach().view(-1), P["attn_sim_w.bias"].detach(),
+                                   P["bn.weight"].detach(), P["bn.bias"].detach(), P["bn.running_mean"],
+                                   P["bn.running_var"], P.get("bn.num_batches_tracked"), env.training)
+            return (out,), dict(sg=sg, sl=sl, saved=saved)
+
+        def bwd(env, st, grads):
+            P = env.P
+            d_sg, d_sl, d_w, d_b, d_bnw, d_bnb = K.saf_bwd(
+                grads[0], st["sg"], st["sl"], P["attn_sim_w.weight"].detach().view(-1), P["attn_sim_w.bias"].detach(),
+                P["bn.weight"].detach(), P["bn.bias"].detach(), P["bn.running_mean"], P["bn.running_var"],
+                env.training, st["saved"])
+            env.grad("attn_sim_w.weight", d_w.view(1, -1))
+            env.grad("attn_sim_w.bias", d_b)
+            env.grad("bn.weight", d_bnw)
+            env.grad("bn.bias", d_bnb)
+            return (torch.cat([d_sg.unsqueeze(1), d_sl], 1),)
+
+        return run_block(self, [sim_emb], fwd, bwd)[0]

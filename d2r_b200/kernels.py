@@ -22,7 +22,7 @@ def gemm(a: Tensor, b: Tensor, c: Tensor, *, m: int, n: int, k: int, lda: int, l
          alpha: float = 1.0, bias: Optional[Tensor] = None, bias_sz: int = 0, act: int = L.ACT_NONE,
          residual: Optional[Tensor] = None, ldr: int = 0, r_str: Tuple[int, int] = (0, 0),
          epilogue: int = L.EPI_STD, c2: Optional[Tensor] = None, accumulate: bool = False, split_k: int = 1,
-         tile_n: int = 0) -> Tensor:
+         tile_n: int = 0, act_cols: int = 0) -> Tensor:
     """C[z] = epilogue(alpha * A[z] (m x k) * B[z]^T (n x k)); strides in elements, (outer, inner)."""
     L.require_cuda(a, b, c, bias, residual, c2)
     if a.dtype != b.dtype:
@@ -37,7 +37,7 @@ def gemm(a: Tensor, b: Tensor, c: Tensor, *, m: int, n: int, k: int, lda: int, l
     g.act, g.epilogue = act, epilogue
     g.r_dtype = L.dt(residual) if residual is not None else 0
     g.accumulate, g.split_k = int(accumulate), split_k
-    g.alpha, g.tile_n = alpha, tile_n
+    g.alpha, g.tile_n, g.act_cols = alpha, tile_n, act_cols
     g.a, g.b, g.c, g.c2 = a.data_ptr(), b.data_ptr(), c.data_ptr(), L.ptr(c2)
     g.bias, g.residual = L.ptr(bias), L.ptr(residual)
     g.lda, g.ldb, g.ldc, g.ldr = lda, ldb, ldc, ldr
@@ -136,14 +136,21 @@ def film_fwd(x: Tensor, st: Tensor) -> Tensor:
     return m
 
 
-def film_bwd(dm: Tensor, x: Tensor, st: Tensor):
+def film_bwd(dm: Tensor, x: Tensor, st: Tensor, add: Optional[Tensor] = None):
+    """dx = dm * s (+ add), d_st = [dm * x * (1 - s^2) | dm]."""
     cols = x.shape[-1]
     rows = x.numel() // cols
     dx = torch.empty_like(x)
     dst = torch.empty_like(st)
-    L.check(L.lib.d2r_film_bwd(dm.data_ptr(), x.data_ptr(), st.data_ptr(), L.dt(x), dx.data_ptr(), dst.data_ptr(),
-                               rows, cols, L.stream()), "film_bwd")
+    L.check(L.lib.d2r_film_bwd(dm.data_ptr(), x.data_ptr(), st.data_ptr(), L.ptr(add), L.dt(x), dx.data_ptr(),
+                               dst.data_ptr(), rows, cols, L.stream()), "film_bwd")
     return dx, dst
+
+
+def mul(x: Tensor, z: Tensor, alpha: float = 1.0) -> Tensor:
+    y = torch.empty_like(x)
+    L.check(L.lib.d2r_mul(x.data_ptr(), z.data_ptr(), L.dt(x), alpha, y.data_ptr(), x.numel(), L.stream()), "mul")
+    return y
 
 
 def axpby(x: Tensor, z: Optional[Tensor], a: float, b: float) -> Tensor:
@@ -152,11 +159,13 @@ def axpby(x: Tensor, z: Optional[Tensor], a: float, b: float) -> Tensor:
     return y
 
 
-def sqdiff_bwd(dsq: Tensor, d: Tensor) -> Tensor:
+def sqdiff_bwd(dsq: Tensor, d: Tensor, add: Optional[Tensor] = None, want_gx: bool = False):
+    """g = 2 d dsq; optionally gx = g + add (gradient of the minuend with an accumulated term)."""
     g = torch.empty_like(d)
-    L.check(L.lib.d2r_sqdiff_bwd(dsq.data_ptr(), d.data_ptr(), L.dt(d), g.data_ptr(), d.numel(), L.stream()),
-            "sqdiff_bwd")
-    return g
+    gx = torch.empty_like(d) if want_gx else None
+    L.check(L.lib.d2r_sqdiff_bwd(dsq.data_ptr(), d.data_ptr(), L.ptr(add), L.dt(d), g.data_ptr(), L.ptr(gx),
+                                 d.numel(), L.stream()), "sqdiff_bwd")
+    return (g, gx) if want_gx else g
 
 
 def pool_mean(xs: Sequence[Tensor]) -> Tensor:
@@ -172,6 +181,14 @@ def pool_mean_bwd(d_pooled: Tensor, Ln: int, dtype: torch.dtype) -> Tensor:
     B, D = d_pooled.shape
     dx = torch.empty(B, Ln, D, device=d_pooled.device, dtype=dtype)
     L.check(L.lib.d2r_pool_mean_bwd(d_pooled.data_ptr(), B, Ln, D, dx.data_ptr(), L.dt(dx), 0, L.stream()),
+            "pool_mean_bwd")
+    return dx
+
+
+def pool_mean_bwd_into(d_pooled: Tensor, dx: Tensor) -> Tensor:
+    """dx[b, l, :] += d_pooled[b, :] / L (in place)."""
+    B, Ln, D = dx.shape
+    L.check(L.lib.d2r_pool_mean_bwd(d_pooled.data_ptr(), B, Ln, D, dx.data_ptr(), L.dt(dx), 1, L.stream()),
             "pool_mean_bwd")
     return dx
 

@@ -71,6 +71,8 @@ typedef struct d2r_gemm_args {
   int32_t split_k;     /* >1: split the k range over CTAs, fp32 C, atomic accumulation */
   float alpha;
   int32_t tile_n;      /* 0 = auto; 64/128/256 forces the tensor-core N tile (tuning knob) */
+  int32_t act_cols;    /* >0: the activation applies to output columns < act_cols only */
+  int32_t reserved0;
   const void* a;
   const void* b;
   void* c;
@@ -166,14 +168,17 @@ int d2r_l2norm_bwd(const void* y, const void* dy, int32_t dtype, const float* rn
  * st is [rows, 2*cols] = [s | t]. */
 int d2r_film_fwd(const void* x, const void* st, int32_t dtype, void* m, int64_t rows, int32_t cols,
                  void* stream);
-/* dm -> dx (+=), d_st = [dm*x*(1-s^2) | dm] */
-int d2r_film_bwd(const void* dm, const void* x, const void* st, int32_t dtype, void* dx, void* d_st,
-                 int64_t rows, int32_t cols, void* stream);
+/* dx = dm*s (+ add, optional), d_st = [dm*x*(1-s^2) | dm] */
+int d2r_film_bwd(const void* dm, const void* x, const void* st, const void* add, int32_t dtype, void* dx,
+                 void* d_st, int64_t rows, int32_t cols, void* stream);
 /* generic y = a*x + b*z elementwise (grad accumulation, residual joins) */
 int d2r_axpby(const void* x, const void* z, int32_t dtype, float a, float b, void* y, int64_t n, void* stream);
 /* squared difference backward (Cells.py:149): sq = d*d with d = x - c saved;  g = 2 d dsq
- * (dx = g, dc = -g) */
-int d2r_sqdiff_bwd(const void* dsq, const void* d, int32_t dtype, void* g, int64_t n, void* stream);
+ * (dc = -g); gx = g (+ add, optional) is the gradient of x, written only when gx != NULL */
+int d2r_sqdiff_bwd(const void* dsq, const void* d, const void* add, int32_t dtype, void* g, void* gx, int64_t n,
+                   void* stream);
+/* y = alpha * x * z elementwise */
+int d2r_mul(const void* x, const void* z, int32_t dtype, float alpha, void* y, int64_t n, void* stream);
 
 /* Attention filtration (XModules.py:380-384) over sim_emb = [global ; local]:
  *   logit[b,l] = w . S[b,l,:] + bias;  BN1d(1) over all B*(L+1) scalars (training: batch

@@ -426,6 +426,15 @@ DEAD_PARAM_SUFFIXES = (".CrossModalAlignment.fc_1.weight", ".CrossModalAlignment
                        ".CrossModalAlignment.fc_2.weight", ".CrossModalAlignment.fc_2.bias")
 
 
+ZERO_GRAD_SUFFIXES = (".CrossModalAlignment.key.bias", ".att_layer.linears.1.bias", ".crcmc.fc_2.bias")
+
+
+def is_zero_grad_param(name: str, training: bool) -> bool:
+    """Parameters whose gradient is mathematically zero (softmax shift invariance of a key-projection bias;
+    a bias in front of train-mode BatchNorm): both sides only hold rounding noise."""
+    return name.endswith(ZERO_GRAD_SUFFIXES) or (training and name.endswith(".SAF_module.attn_sim_w.bias"))
+
+
 def is_dead_param(name: str) -> bool:
     """Parameters that never receive a gradient in the reference."""
     return name.endswith(DEAD_PARAM_SUFFIXES) or name.startswith(("path_mapping.", "bn."))

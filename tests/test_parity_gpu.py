@@ -1,0 +1,205 @@
+"""Parity of the CUDA stack (through the nn.Module drop-in API -> C ABI) with
+(1) golden vectors produced by the unmodified reference (tests/golden/*.npz) and
+(2) the CPU oracle on the same seeded inputs at larger sizes.
+
+Tolerances (BASELINE.json north_star): routing probabilities and outputs within 1e-5 relative in the fp32
+mode (measured on each tensor's own max-abs scale; 2e-5 to leave room for summation-order differences
+between CPU and GPU fp32), 2e-2 in the bf16 mode; gradients looser because they pass through
+softmax(3.6 q.k)."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import d2r_oracle as O
+from tests.golden.cases import CASES, PARAM_SEED_BASE, INPUT_SEED_BASE, LOSS_SEED
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_args():
+    return argparse.Namespace(embed_size=768, hid_router=768, hid_IMRC=768, num_head_IMRC=16,
+                              raw_feature_norm_CMRC="clipped_l2norm", lambda_softmax_CMRC=4.0, alpha=0, margin=0.1,
+                              bert_name="bert-base-uncased", vit_name="clip-vit-base-patch32")
+
+
+def build(R, K, rev, params, training):
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule
+    cls = Reversed_InteractionModule if rev else InteractionModule
+    m = cls(make_args(), num_layer_routing=R, num_cells=K, path_hid=128)
+    m.load_state_dict(params)
+    m = m.cuda()
+    m.train(training)
+    return m
+
+
+def relerr(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def digest(t):
+    f = t.detach().double().flatten().cpu()
+    idx = torch.linspace(0, f.numel() - 1, 16).long()
+    return torch.cat([f.sum().view(1), f.abs().sum().view(1), f[idx]]).numpy()
+
+
+def run_cuda(m, text, image, bf16, w_out, w_sim):
+    t = text.cuda().requires_grad_(True)
+    i = image.cuda().requires_grad_(True)
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if bf16 else torch.autocast("cuda", enabled=False)
+    with ctx:
+        out, sim, probs = m(t, i, return_path_probs=True)
+    loss = (out[0] * w_out.cuda()).sum() + (sim * w_sim.cuda()).sum()
+    loss.backward()
+    return out[0], sim, probs, t.grad, i.grad
+
+
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_against_reference_golden(case, bf16):
+    name, B, Lt, Li, R, rev, training, realistic, scale = case
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    P = O.make_params(PARAM_SEED_BASE + R, R, 6, scale)
+    m = build(R, 6, rev, P, training)
+    text, image = O.make_inputs(INPUT_SEED_BASE + B, B, Lt, Li, realistic=realistic)
+    g = torch.Generator().manual_seed(LOSS_SEED)
+    w_out = torch.randn(gold["out"].shape, generator=g)
+    w_sim = torch.randn(gold["sim"].shape, generator=g)
+    out, sim, probs, d_text, d_image = run_cuda(m, text, image, bf16, w_out, w_sim)
+    assert out.dtype == torch.float32 and sim.dtype == torch.float32
+    p_tol = 2e-2 if bf16 else 2e-5
+    for li, p in enumerate(probs):
+        assert relerr(p, gold[f"probs{li}"]) <= p_tol, ("probs", li, relerr(p, gold[f"probs{li}"]))
+    assert relerr(sim, gold["sim"]) <= 2 * p_tol
+    # the realistic cases push x20 outlier channels through softmax(3.6 q.k): bf16 is only judged on routing
+    o_tol = (0.25 if realistic else 5e-2) if bf16 else 1e-4
+    assert relerr(out, gold["out"]) <= o_tol, ("out", relerr(out, gold["out"]))
+    if not bf16:
+        assert relerr(d_text, gold["d_text"]) <= 2e-3, ("d_text", relerr(d_text, gold["d_text"]))
+        assert relerr(d_image, gold["d_image"]) <= 2e-3, ("d_image", relerr(d_image, gold["d_image"]))
+        dead = set(gold["dead"].tolist())
+        worst = ("", 0.0)
+        for k, p in m.named_parameters():
+            if k in dead:
+                assert p.grad is None, k
+                continue
+            assert p.grad is not None, k
+            ref, got = gold["gd/" + k], digest(p.grad)
+            if O.is_zero_grad_param(k, training):
+                assert abs(got[1]) < 1e-1, k      # mathematically-zero gradient: noise on both sides
+                continue
+            e = abs(got[1] - ref[1]) / abs(ref[1])
+            e = max(e, np.abs(got[2:] - ref[2:]).max() / (np.abs(ref[2:]).max() + 1e-30))
+            if e > worst[1]:
+                worst = (k, e)
+        assert worst[1] <= 5e-3, worst
+        for k in gold.files:
+            if k.startswith("buf/"):
+                got = m.state_dict()[k[4:]].cpu().numpy()
+                np.testing.assert_allclose(got, gold[k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("rev", [False, True], ids=["text", "image"])
+def test_config1_fp32_vs_oracle(rev):
+    """BASELINE config 1 shape: batch 8, text 128 + 50 image tokens, hidden 768, K=6, R=3, fp32."""
+    B, Lt, Li, R = 8, 128, 50, 3
+    P = O.make_params(11, R, 6)
+    text, image = O.make_inputs(2023, B, Lt, Li)
+    ref_out, ref_sim, ref_probs = O.stack_forward(P, text, image, R, 6, rev, training=False)
+    m = build(R, 6, rev, P, training=False)
+    with torch.no_grad():
+        out, sim, probs = m(text.cuda(), image.cuda(), return_path_probs=True)
+    for a, b in zip(probs, ref_probs):
+        assert relerr(a, b) <= 2e-5, relerr(a, b)
+    assert relerr(sim, ref_sim) <= 2e-5
+    assert relerr(out[0], ref_out[0]) <= 1e-4
+    # argmax over the hidden dimension of the CLS row (a stand-in for "argmax predictions"): bit-exact
+    assert torch.equal(out[0][:, 0].argmax(-1).cpu(), ref_out[0][:, 0].argmax(-1))
+
+
+@pytest.mark.parametrize("K,R", [(4, 2), (4, 3), (6, 2)])
+def test_reference_derived_shapes_vs_oracle(K, R):
+    B, Lt, Li = 3, 24, 9
+    P = O.make_params(5, R, K)
+    text, image = O.make_inputs(17, B, Lt, Li)
+    for k, v in P.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    t, i = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+    ref_out, ref_sim, ref_probs = O.stack_forward(P, t, i, R, K, False, training=True, bn_updates={})
+    (ref_out[0].sum() + ref_sim.sum()).backward()
+    m = build(R, K, False, {k: v.detach() for k, v in P.items()}, training=True)
+    tc, ic = text.cuda().requires_grad_(True), image.cuda().requires_grad_(True)
+    out, sim, probs = m(tc, ic, return_path_probs=True)
+    (out[0].sum() + sim.sum()).backward()
+    for a, b in zip(probs, ref_probs):
+        assert relerr(a, b.detach()) <= 2e-5
+    assert relerr(out[0], ref_out[0].detach()) <= 1e-4
+    assert relerr(tc.grad, t.grad) <= 2e-3 and relerr(ic.grad, i.grad) <= 2e-3
+
+
+def test_gate_known_answer():
+    """All routers dead (W2 = 0, b2 = -5): layer-0 outputs == relu(text) exactly, sim_paths == 0."""
+    from d2r_b200.interaction.DynamicInteraction import DynamicInteraction_Layer0
+    P = O.make_params(1, 3, 6)
+    for k in P:
+        if k.endswith("router.mlp.2.weight"):
+            P[k].zero_()
+        if k.endswith("router.mlp.2.bias"):
+            P[k].fill_(-5.0)
+    text, image = O.make_inputs(3, 2, 6, 4)
+    m = build(3, 6, False, P, training=False)
+    with torch.no_grad():
+        outs, allp = m.dynamic_itr_l0(text.cuda(), image.cuda())
+        assert len(outs) == 6 and allp.shape == (2, 6, 6)
+        for o in outs:
+            assert torch.equal(o.cpu(), torch.relu(text))
+        out, sim = m(text.cuda(), image.cuda())
+    assert torch.isfinite(out[0]).all() and torch.equal(sim.cpu(), torch.zeros(2, 2))
+
+
+def test_eval_per_sample_independent_and_deterministic():
+    P = O.make_params(5, 3, 6)
+    text, image = O.make_inputs(11, 4, 16, 5)
+    m = build(3, 6, False, P, training=False)
+    with torch.no_grad():
+        a, sa = m(text.cuda(), image.cuda())
+        a2, _ = m(text.cuda(), image.cuda())
+        b, _ = m(text[:2].cuda(), image[:2].cuda())
+    assert torch.equal(a[0], a2[0])
+    assert torch.equal(a[0][:2], b[0])
+
+
+def test_submodules_standalone_vs_oracle():
+    """The individual reference classes stay usable on their own (cells, router, self-attention...)."""
+    P = O.make_params(9, 3, 6)
+    text, image = O.make_inputs(4, 3, 10, 7)
+    m = build(3, 6, False, P, training=False)
+    L0 = m.dynamic_itr_l0
+    tc, ic = text.cuda(), image.cuda()
+    pre = "dynamic_itr_l0"
+    with torch.no_grad():
+        pairs = [
+            (L0.ric(tc), O.cell_ric(text, P, pre + ".ric")),
+            (L0.imrc(tc), O.cell_imrc(text, P, pre + ".imrc")),
+            (L0.cmrc(tc, ic), O.cell_cmrc(text, image, P, pre + ".cmrc")),
+            (L0.glac(tc, ic), O.cell_glac(text, image, P, pre + ".glac", training=False)),
+            (L0.crcmc(tc, ic), O.cell_crcmc(text, image, P, pre + ".crcmc")),
+            (L0.gesc(tc, ic), O.cell_gesc(text, image, P, pre + ".gesc")),
+        ]
+    for (emb, prob), (remb, rprob) in pairs:
+        assert relerr(prob, rprob) <= 2e-5
+        assert relerr(emb, remb) <= 1e-4
+
+
+def test_cpu_tensors_are_rejected():
+    P = O.make_params(5, 3, 6)
+    m = build(3, 6, False, P, training=False)
+    text, image = O.make_inputs(11, 2, 8, 5)
+    with pytest.raises(RuntimeError):
+        m(text, image)

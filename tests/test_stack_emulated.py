@@ -1,0 +1,144 @@
+"""CPU check of the product's host-side logic: stack.py / autograd.py / the nn.Module mirror are executed
+with the CUDA kernels replaced by the torch-CPU emulation in tests/emu_kernels.py (test infrastructure, see
+its header) and compared with the reference-generated golden vectors and the oracle.  This pins the launch
+sequence, the stride bookkeeping and the hand-written backward pass without a GPU; the kernels themselves
+are checked on the GPU (-m gpu)."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import d2r_oracle as O
+from tests import emu_kernels as E
+from tests.golden.cases import CASES, PARAM_SEED_BASE, INPUT_SEED_BASE, LOSS_SEED
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    from d2r_b200 import build
+    build.build()
+    import d2r_b200.kernels as K
+    import d2r_b200.autograd as A
+    for name in dir(E):
+        if not name.startswith("_") and callable(getattr(E, name)) and hasattr(K, name):
+            monkeypatch.setattr(K, name, getattr(E, name))
+    monkeypatch.setattr(A, "_require_cuda", lambda inputs: None)
+    yield
+
+
+def make_args():
+    return argparse.Namespace(embed_size=768, hid_router=768, hid_IMRC=768, num_head_IMRC=16,
+                              raw_feature_norm_CMRC="clipped_l2norm", lambda_softmax_CMRC=4.0, alpha=0, margin=0.1,
+                              bert_name="bert-base-uncased", vit_name="clip-vit-base-patch32")
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def digest(t):
+    f = t.detach().double().flatten()
+    idx = torch.linspace(0, f.numel() - 1, 16).long()
+    return torch.cat([f.sum().view(1), f.abs().sum().view(1), f[idx]]).numpy()
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[2]], ids=[c[0] for c in CASES[:3]])
+def test_emulated_stack_matches_reference_golden(emulated, case):
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule
+    name, B, Lt, Li, R, rev, training, realistic, scale = case
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    P = O.make_params(PARAM_SEED_BASE + R, R, 6, scale)
+    m = (Reversed_InteractionModule if rev else InteractionModule)(make_args(), R, 6, 128)
+    m.load_state_dict(P)
+    m.train(training)
+    text, image = O.make_inputs(INPUT_SEED_BASE + B, B, Lt, Li, realistic=realistic)
+    text.requires_grad_(True)
+    image.requires_grad_(True)
+    g = torch.Generator().manual_seed(LOSS_SEED)
+    w_out = torch.randn(gold["out"].shape, generator=g)
+    w_sim = torch.randn(gold["sim"].shape, generator=g)
+    out, sim, probs = m(text, image, return_path_probs=True)
+    ((out[0] * w_out).sum() + (sim * w_sim).sum()).backward()
+    for li, p in enumerate(probs):
+        assert relerr(p, gold[f"probs{li}"]) < 1e-5
+    assert relerr(out[0], gold["out"]) < 1e-5 and relerr(sim, gold["sim"]) < 1e-5
+    assert relerr(text.grad, gold["d_text"]) < 1e-4, relerr(text.grad, gold["d_text"])
+    assert relerr(image.grad, gold["d_image"]) < 1e-4, relerr(image.grad, gold["d_image"])
+    dead = set(gold["dead"].tolist())
+    for k, p in m.named_parameters():
+        if k in dead:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        ref, got = gold["gd/" + k], digest(p.grad)
+        if O.is_zero_grad_param(k, training):
+            assert abs(got[1]) < 1e-2, k
+            continue
+        assert abs(got[1] - ref[1]) <= 1e-3 * abs(ref[1]), (k, got[1], ref[1])
+        assert np.abs(got[2:] - ref[2:]).max() <= 1e-3 * np.abs(ref[2:]).max() + 1e-7, k
+    for k in gold.files:
+        if k.startswith("buf/"):
+            np.testing.assert_allclose(m.state_dict()[k[4:]].numpy(), gold[k], rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+@pytest.mark.parametrize("K,R", [(4, 2), (6, 2)])
+def test_emulated_reference_derived(emulated, K, R):
+    from d2r_b200.interaction import InteractionModule
+    B, Lt, Li = 3, 10, 6
+    P = O.make_params(5, R, K)
+    text, image = O.make_inputs(17, B, Lt, Li)
+    t, i = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+    ref_out, ref_sim, _ = O.stack_forward(P, t, i, R, K, False, training=True, bn_updates={})
+    (ref_out[0].sum() + ref_sim.sum()).backward()
+    m = InteractionModule(make_args(), R, K, 128)
+    m.load_state_dict(P)
+    t2, i2 = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+    out, sim = m(t2, i2)
+    (out[0].sum() + sim.sum()).backward()
+    assert relerr(out[0], ref_out[0].detach()) < 1e-5 and relerr(sim, ref_sim.detach()) < 1e-5
+    assert relerr(t2.grad, t.grad) < 1e-4 and relerr(i2.grad, i.grad) < 1e-4
+
+
+def test_emulated_submodules(emulated):
+    """Stand-alone use of the mirrored classes (cells / layer), forward and backward, against the oracle."""
+    from d2r_b200.interaction import InteractionModule
+    P = O.make_params(9, 3, 6)
+    m = InteractionModule(make_args(), 3, 6, 128)
+    m.load_state_dict(P)
+    m.eval()
+    L0, pre = m.dynamic_itr_l0, "dynamic_itr_l0"
+    text, image = O.make_inputs(4, 3, 10, 7)
+    cells = [
+        (lambda t, i: L0.ric(t), lambda t, i: O.cell_ric(t, P, pre + ".ric")),
+        (lambda t, i: L0.imrc(t), lambda t, i: O.cell_imrc(t, P, pre + ".imrc")),
+        (lambda t, i: L0.cmrc(t, i), lambda t, i: O.cell_cmrc(t, i, P, pre + ".cmrc")),
+        (lambda t, i: L0.glac(t, i), lambda t, i: O.cell_glac(t, i, P, pre + ".glac", training=False)),
+        (lambda t, i: L0.crcmc(t, i), lambda t, i: O.cell_crcmc(t, i, P, pre + ".crcmc")),
+        (lambda t, i: L0.gesc(t, i), lambda t, i: O.cell_gesc(t, i, P, pre + ".gesc")),
+    ]
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(3, 10, 768, generator=g)
+    wp = torch.randn(3, 6, generator=g)
+    for ci, (mine, ref) in enumerate(cells):
+        ta, ia = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+        tb, ib = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+        e1, p1 = mine(ta, ia)
+        e2, p2 = ref(tb, ib)
+        assert relerr(e1, e2.detach()) < 1e-5 and relerr(p1, p2.detach()) < 1e-5, ci
+        ((e1 * w).sum() + (p1 * wp).sum()).backward()
+        ((e2 * w).sum() + (p2 * wp).sum()).backward()
+        assert relerr(ta.grad, tb.grad) < 1e-4, ci
+        if ib.grad is not None:
+            assert relerr(ia.grad, ib.grad) < 1e-4, ci
+    # a routing layer on its own
+    outs, allp = L0(text, image)
+    embs, probs = O.run_cells([text] * 6, image, P, pre, 6, False, None, False)
+    r_outs, r_allp = O.aggregate_multi(embs, probs, 6)
+    assert relerr(allp, r_allp) < 1e-5
+    for a, b in zip(outs, r_outs):
+        assert relerr(a, b) < 1e-5
