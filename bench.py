@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Benchmark of the routed interaction stack (BASELINE.json metric: routed-interaction samples/sec,
+forward + backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  # this repo's CUDA stack
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference algorithm on CPU
+
+Workload (BASELINE.json configs[1]): both branch stacks (text branch + image branch, K=6 cells, R=3 routing
+layers, text 128 + 50 image tokens, hidden 768), bf16 arithmetic with fp32 accumulation, batch 256 per
+GPU, one step = forward + backward of both stacks (loss = out.sum() + sim_paths.sum() per branch,
+SURVEY §8d) + the data-parallel gradient all-reduce when N > 1.  Synthetic N(0,1) inputs, reference
+default-init weights.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step driven from
+pinned HOST buffers through the nn.Module API with the H2D copy of the inputs and a D2H read of the loss
+inside the timed region.  `roofline`: all tcgen05 GEMM launches of a step, algorithmic FLOPs (2*m*n*k per
+problem, no padding) over their CUDA-event durations, against the measured bf16 peak in MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port (oracle/d2r_oracle.py, with the reference's discarded reverse-attention
+branch executed so that it pays the reference's real cost) on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LT, LI, D, KC, R = 128, 50, 768, 6, 3
+BATCH_PER_GPU = 256
+CPU_SAMPLE_BATCH = 8
+
+
+def make_args():
+    return argparse.Namespace(embed_size=768, hid_router=768, hid_IMRC=768, num_head_IMRC=16,
+                              raw_feature_norm_CMRC="clipped_l2norm", lambda_softmax_CMRC=4.0, alpha=0, margin=0.1,
+                              bert_name="bert-base-uncased", vit_name="clip-vit-base-patch32")
+
+
+def useful_flops_per_sample(Lt=LT, Li=LI, layers=R):
+    """useful forward FLOPs per sample for both branches (dead branch excluded); bwd = 2x fwd."""
+    def layer(Lq, Lc):
+        lin = lambda L_: 2 * L_ * D * D
+        cma = lin(Lq) + 2 * lin(Lc) + 4 * Lq * Lc * D
+        imrc = 5 * lin(Lq) + 4 * Lq * Lq * D
+        glac = cma + 2 * lin(Lq) + 8 * D * D + 4 * (Lq + 1) * D
+        cmrc = cma + 4 * lin(Lq)
+        crcmc = cma + 4 * lin(Lq) + 4 * Lq * Lq * D
+        gesc = 8 * D * D
+        router = 6 * (2 * D * 768 + 2 * 768 * KC + Lq * D)
+        agg = 2 * KC * KC * Lq * D
+        return cma * 0 + imrc + glac + cmrc + crcmc + gesc + router + agg
+    return layers * (layer(Lt, Li) + layer(Li, Lt))
+
+
+# ----------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_fn(batch, threads=None):
+    """One fwd+bwd of both branch stacks with the oracle port (reference algorithm incl. its dead branch)."""
+    import torch
+    from oracle import d2r_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    Pt = O.make_params(2023, R, KC)
+    Pi = O.make_params(2024, R, KC)
+    for P in (Pt, Pi):
+        for k, v in P.items():
+            if v.is_floating_point() and "running" not in k and not O.is_dead_param(k):
+                v.requires_grad_(True)
+    text, image = O.make_inputs(2023, batch, LT, LI)
+    text.requires_grad_(True)
+    image.requires_grad_(True)
+
+    def step():
+        for P in (Pt, Pi):
+            for v in P.values():
+                v.grad = None
+        text.grad = None
+        image.grad = None
+        o1, s1, _ = O.stack_forward(Pt, text, image, R, KC, False, True, {}, dead_branch=True)
+        o2, s2, _ = O.stack_forward(Pi, text, image, R, KC, True, True, {}, dead_branch=True)
+        loss = o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def run_cpu_reference(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    import torch
+    cores = os.cpu_count() or 1
+    step = cpu_reference_step_fn(batch, cores)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return dict(value=batch * steps / total, ms_per_step=1e3 * total / steps, cores=cores, threads=torch.get_num_threads(),
+                sample=f"{steps} timed steps of batch {batch} (both branch stacks fwd+bwd, fp32, torch CPU, "
+                       f"dead reverse-attention branch executed), {warmup} warm-up")
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    steps = max(1, args.steps)
+    # bound the run: each step is ~B=8 samples; never more than ~3 minutes of CPU work
+    r = run_cpu_reference(min(steps, 40), min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": "routed-interaction samples/sec fwd+bwd", "value": r["value"],
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": min(steps, 40), "warmup": min(args.warmup, 3),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus) | {"cpu_sample_batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "D2R routed interaction stack, both branches (text+image), bf16 fwd+bwd, K=6 cells, "
+                        "R=3 routing layers, text 128 + 50 image tokens, hidden 768 (BASELINE configs[1])",
+            "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus, "text_len": LT, "image_tokens": LI,
+            "hidden": D, "cells": KC, "routing_layers": R, "parallelism": f"dp{n_gpus}",
+            "l2": "no explicit flush: the per-step working set (several GB of activations) is far larger "
+                  "than the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- own arm
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+    from d2r_b200 import kernels as K
+    from d2r_b200.dp import GradAllReducer
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = BATCH_PER_GPU
+
+    torch.manual_seed(2023)
+    a = make_args()
+    mt = InteractionModule(a, R, KC, 128).to(dev).train()
+    mi = Reversed_InteractionModule(a, R, KC, 128).to(dev).train()
+    reducer = GradAllReducer([mt, mi])
+
+    g = torch.Generator().manual_seed(2023 + rank)
+    h_text = torch.randn(B, LT, D, generator=g).pin_memory()
+    h_image = torch.randn(B, LI, D, generator=g).pin_memory()
+    d_text = torch.empty(B, LT, D, device=dev, requires_grad=True)
+    d_image = torch.empty(B, LI, D, device=dev, requires_grad=True)
+    h_loss = torch.empty(1).pin_memory()
+    with torch.no_grad():
+        d_text.copy_(h_text)
+        d_image.copy_(h_image)
+
+    def fwd_bwd():
+        d_text.grad = None
+        d_image.grad = None
+        for m in (mt, mi):
+            for p in m.parameters():
+                p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o1, s1 = mt(d_text, d_image)
+            o2, s2 = mi(d_text, d_image)
+        loss = o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()
+        loss.backward()
+        return loss
+
+    # --- optional CUDA graph of fwd+bwd (+ gradient packing) --------------------------------------
+    graph, static_loss = None, None
+    side = torch.cuda.Stream()
+    use_graph = not args.no_graph
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            loss = fwd_bwd()
+            reducer.pack()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = fwd_bwd()
+                reducer.pack()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:   # report and continue eagerly
+            sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
+            graph = None
+            torch.cuda.synchronize()
+
+    def step(from_host):
+        if from_host:
+            with torch.no_grad():
+                d_text.copy_(h_text, non_blocking=True)
+                d_image.copy_(h_image, non_blocking=True)
+        if graph is not None:
+            graph.replay()
+            loss = static_loss
+        else:
+            loss = fwd_bwd()
+            reducer.pack()
+        reducer.all_reduce()
+        if from_host:
+            h_loss.copy_(loss.detach().float().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = K.L.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step(from_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = K.L.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(False, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step(True)
+    ms_e2e, _ = timed(True, args.steps)
+    eager_launches_per_step = None
+    if graph is not None:
+        # kernels launched from a replayed graph do not pass through the C ABI: count one eager step
+        n0 = K.L.launch_count()
+        fwd_bwd()
+        torch.cuda.synchronize()
+        eager_launches_per_step = K.L.launch_count() - n0
+        launches = eager_launches_per_step * args.steps
+
+    # --- per-kernel roofline pass (separate, eager, CUDA events around every C-ABI GEMM launch) -----
+    roof, hbm = kernel_roofline(fwd_bwd, K, torch) if rank == 0 else (None, None)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback"
+        samples = B * world * args.steps
+        value = samples / (ms / 1e3)
+        flops_step = 3 * useful_flops_per_sample() * B
+        cpu = None
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample"], capture_output=True,
+                                 text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {e}"}
+        line = {
+            "metric": "routed-interaction samples/sec fwd+bwd", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world) | {"cuda_graph": graph is not None},
+            "clocks": clocks,
+            "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": (h_text.numel() + h_image.numel()) * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one fwd+bwd step)",
+                "achieved": roof["tflops"], "peak": tc_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tc_peak,
+                "traffic": None, "peak_source": peak_src, "launches_per_step": roof["launches"],
+                "kernel_ms_per_step": roof["ms"], "kernel_share_of_step": roof["ms"] / (ms / args.steps),
+                "step_algorithmic_tflops": flops_step / (ms / args.steps / 1e3) / 1e12,
+                "step_frac_of_peak": flops_step / (ms / args.steps / 1e3) / 1e12 / tc_peak,
+            },
+            "roofline_hbm": {"bound": "hbm", "kernel": "agg_fwd_kernel / agg_bwd_kernel (aggregation epilogue)",
+                             "achieved": hbm["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm["gbs"] / hbm_peak,
+                             "launches_per_step": hbm["launches"], "kernel_ms_per_step": hbm["ms"]},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_roofline(fwd_bwd, K, torch):
+    """Run two eager steps with CUDA events around each tcgen05 GEMM and each aggregation launch."""
+    recs = {"gemm": [], "agg": []}
+    orig_gemm, orig_af, orig_ab = K.gemm, K.aggregate_fwd, K.aggregate_bwd
+
+    def timed_call(kind, work, fn, *a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **kw)
+        e1.record()
+        recs[kind].append((e0, e1, work))
+        return r
+
+    def gemm(a, b, c, **kw):
+        if a.dtype != torch.bfloat16:
+            return orig_gemm(a, b, c, **kw)
+        return timed_call("gemm", 2.0 * kw["m"] * kw["n"] * kw["k"] * kw.get("batch", 1), orig_gemm, a, b, c, **kw)
+
+    def agg_f(full, bvec, P, gate, final, inputs=None, want_pooled=True):
+        x0 = full[0]
+        nfull = sum(f is not None for f in full)
+        n_out = 1 if final else len(full)
+        byts = (nfull + n_out) * x0.numel() * x0.element_size()
+        return timed_call("agg", byts, orig_af, full, bvec, P, gate, final, inputs, want_pooled)
+
+    def agg_b(full, bvec, P, gate, final, d_outs, d_pooled, inputs=None, want_d_inputs=False):
+        x0 = full[0]
+        nfull = sum(f is not None for f in full)
+        n_out = 1 if final else len(full)
+        extra = (len(full) - 1) if (final and want_d_inputs) else 0
+        byts = (n_out + 2 * nfull + extra) * x0.numel() * x0.element_size()
+        return timed_call("agg", byts, orig_ab, full, bvec, P, gate, final, d_outs, d_pooled, inputs, want_d_inputs)
+
+    K.gemm, K.aggregate_fwd, K.aggregate_bwd = gemm, agg_f, agg_b
+    try:
+        fwd_bwd()                       # warm
+        torch.cuda.synchronize()
+        for v in recs.values():
+            v.clear()
+        nsteps = 2
+        for _ in range(nsteps):
+            fwd_bwd()
+        torch.cuda.synchronize()
+    finally:
+        K.gemm, K.aggregate_fwd, K.aggregate_bwd = orig_gemm, orig_af, orig_ab
+    gms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["gemm"]) / nsteps
+    gfl = sum(w for _, _, w in recs["gemm"]) / nsteps
+    ams = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["agg"]) / nsteps
+    aby = sum(w for _, _, w in recs["agg"]) / nsteps
+    return ({"tflops": gfl / (gms / 1e3) / 1e12, "ms": gms, "launches": len(recs["gemm"]) // nsteps},
+            {"gbs": aby / (ams / 1e3) / 1e9, "ms": ams, "launches": len(recs["agg"]) // nsteps})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.cpu_sample:
+        r = run_cpu_reference(steps=4, warmup=1)
+        print(json.dumps({"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                          "sample": r["sample"]}))
+        return 0
+    if args.impl == "reference":
+        return reference_arm(args)
+    return own_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
