@@ -11,6 +11,8 @@
 // same kernel serves forward (x W^T), data-gradient (dy W) and weight-gradient (dy^T x).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -31,7 +33,8 @@ struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int BIAS_BYTES = 4 * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
 struct TcParams {
@@ -46,7 +49,7 @@ struct TcParams {
   const void* residual;
   long long ldc, ldr, c_so, c_si, r_so, r_si, bias_sz;
   float alpha;
-  int act, epilogue, c_dtype, r_dtype, atomic, act_cols;
+  int act, epilogue, c_dtype, r_dtype, atomic, act_cols, variant;
 };
 
 struct TileCoord {
@@ -71,43 +74,43 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long t,
   return tc;
 }
 
-template <typename TC>
-__device__ __forceinline__ void store_group(TC* cptr, const float (&v)[8], int nvalid, bool atomic) {
-  if (atomic) {
-    if constexpr (sizeof(TC) == 4) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nvalid) atomicAdd(reinterpret_cast<float*>(cptr) + i, v[i]);
-    }
-    return;
-  }
-  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(cptr) & 15) == 0) {
-    store8(cptr, v);
+// ------------------------------------------------------------------ epilogue
+// Variants are compiled as separate straight-line loops (one dispatch per kernel) so that the hot
+// loop stays small enough for the instruction cache; MODE 0 = bias/act/residual, 1 = squared
+// difference (two outputs), 2 = fp32 atomic accumulation (split-K / accumulate).
+struct NoRes {};
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T>
+__device__ __forceinline__ void st_group(T* ptr, const float (&v)[8], int nvalid) {
+  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+    store8(ptr, v);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (i < nvalid) Elem<TC>::st(cptr + i, v[i]);
+      if (i < nvalid) Elem<T>::st(ptr + i, v[i]);
   }
 }
 
-template <typename TR>
-__device__ __forceinline__ void load_group(const TR* rptr, float (&v)[8], int nvalid) {
-  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(rptr) & 15) == 0) {
-    load8(rptr, v);
+template <typename T>
+__device__ __forceinline__ void ld_group(const T* ptr, float (&v)[8], int nvalid) {
+  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+    load8(ptr, v);
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (i < nvalid) ? Elem<TR>::ld(rptr + i) : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = (i < nvalid) ? Elem<T>::ld(ptr + i) : 0.f;
   }
 }
 
-// one thread: 32 consecutive accumulator columns of one output row
-__device__ __forceinline__ void epilogue_row(const TcParams& p, const uint32_t (&r)[32], long long row, int col0,
-                                             const TileCoord& tc) {
-  const long long c_off = static_cast<long long>(tc.zo) * p.c_so + static_cast<long long>(tc.zi) * p.c_si +
-                          row * p.ldc;
-  const long long r_off = static_cast<long long>(tc.zo) * p.r_so + static_cast<long long>(tc.zi) * p.r_si +
-                          row * p.ldr;
-  const float* bias = p.bias ? p.bias + static_cast<long long>(tc.z) * p.bias_sz : nullptr;
+// one thread: 32 consecutive accumulator columns (col0 .. col0+31) of one output row
+template <typename CT, typename RT, int MODE>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&r)[32], const float* sbias,
+                                               CT* crow, CT* c2row, const RT* rrow, int col0) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int col = col0 + g * 8;
@@ -116,46 +119,102 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const uint32_t (
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(r[g * 8 + i]);
-    if (bias) {
+    if (sbias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if constexpr (MODE == 2) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (i < nvalid) v[i] += __ldg(bias + col + i);
-    }
-    float res[8];
-    if (p.residual) {
-      if (p.r_dtype == D2R_BF16)
-        load_group(reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col, res, nvalid);
-      else
-        load_group(reinterpret_cast<const float*>(p.residual) + r_off + col, res, nvalid);
-    }
-    if (p.epilogue == D2R_EPI_SQDIFF) {
-      float d[8];
+        if (i < nvalid) atomicAdd(reinterpret_cast<float*>(crow) + col + i, v[i]);
+    } else if constexpr (MODE == 1) {
+      float res[8], d[8];
+      ld_group(rrow + col, res, nvalid);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         d[i] = res[i] - v[i];
         v[i] = d[i] * d[i];
       }
-      if (p.c_dtype == D2R_BF16)
-        store_group(reinterpret_cast<__nv_bfloat16*>(p.c2) + c_off + col, d, nvalid, false);
-      else
-        store_group(reinterpret_cast<float*>(p.c2) + c_off + col, d, nvalid, false);
+      st_group(c2row + col, d, nvalid);
+      st_group(crow + col, v, nvalid);
     } else {
+      if (p.act != D2R_ACT_NONE && (p.act_cols == 0 || col < p.act_cols)) {
+        if (p.act == D2R_ACT_RELU) {
 #pragma unroll
-      if (p.act_cols == 0 || col < p.act_cols) {
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
+          for (int i = 0; i < 8; ++i) v[i] = sizeof(CT) == 2 ? fast_tanh(v[i]) : tanhf(v[i]);
+        }
       }
-      if (p.residual) {
+      if constexpr (!std::is_same<RT, NoRes>::value) {
+        float res[8];
+        ld_group(rrow + col, res, nvalid);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += res[i];
       }
+      st_group(crow + col, v, nvalid);
     }
-    if (p.c_dtype == D2R_BF16)
-      store_group(reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + col, v, nvalid, false);
-    else
-      store_group(reinterpret_cast<float*>(p.c) + c_off + col, v, nvalid, p.atomic != 0);
   }
 }
+
+template <int BN, typename CT, typename RT, int MODE>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, float* sbias_warp, int q, int lane) {
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const TileCoord tc = decode_tile(p, t, BN);
+    // stage this tile's bias slice in shared memory while the accumulator is still being produced
+    if (p.bias) {
+      const float* bias = p.bias + static_cast<long long>(tc.z) * p.bias_sz;
+      for (int i = lane; i < BN; i += 32) sbias_warp[i] = (tc.n0 + i < p.n) ? __ldg(bias + tc.n0 + i) : 0.f;
+    }
+    __syncwarp();
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+    const long long row = tc.m0 + q * 32 + lane;
+    const bool row_ok = row < p.m;
+    const long long c_off = static_cast<long long>(tc.zo) * p.c_so + static_cast<long long>(tc.zi) * p.c_si +
+                            row * p.ldc;
+    CT* crow = reinterpret_cast<CT*>(p.c) + c_off;
+    CT* c2row = MODE == 1 ? reinterpret_cast<CT*>(p.c2) + c_off : nullptr;
+    const RT* rrow = nullptr;
+    if constexpr (!std::is_same<RT, NoRes>::value)
+      rrow = reinterpret_cast<const RT*>(p.residual) + static_cast<long long>(tc.zo) * p.r_so +
+             static_cast<long long>(tc.zi) * p.r_si + row * p.ldr;
+    const int ncols = min(BN, p.n - tc.n0);
+    const int nchunks = (ncols + 31) >> 5;
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t ra[32], rb[32];
+    tmem_ld32(taddr, ra);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c += 2) {
+      tmem_ld_wait();
+      if (c + 1 < nchunks) tmem_ld32(taddr + (c + 1) * 32, rb);
+      if (row_ok)
+        epilogue_chunk<CT, RT, MODE>(p, ra, p.bias ? sbias_warp + c * 32 : nullptr, crow, c2row, rrow, tc.n0 + c * 32);
+      if (c + 1 < nchunks) {
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld32(taddr + (c + 2) * 32, ra);
+        if (row_ok)
+          epilogue_chunk<CT, RT, MODE>(p, rb, p.bias ? sbias_warp + (c + 1) * 32 : nullptr, crow, c2row, rrow,
+                                       tc.n0 + (c + 1) * 32);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
+enum EpiVariant {
+  EV_F32 = 0, EV_F32_RF32, EV_F32_RBF16, EV_BF16, EV_BF16_RF32, EV_BF16_RBF16, EV_SQ_F32, EV_SQ_BF16, EV_ATOMIC
+};
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
@@ -171,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);   // [4][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,27 +337,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------- epilogue (4 warps)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t, BN);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const long long row = tc.m0 + q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = tc.n0 + c * 32;
-        if (col0 >= p.n) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + static_cast<uint32_t>(acc * BN + c * 32) + (static_cast<uint32_t>(q * 32) << 16), r);
-        tmem_ld_wait();
-        if (row < p.m) epilogue_row(p, r, row, col0, tc);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+    float* sb = sbias + (warp - 2) * BN;
+    using bf16 = __nv_bfloat16;
+    switch (p.variant) {
+      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      default:            epilogue_loop<BN, float, NoRes, 2>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
     }
   }
 
@@ -414,6 +465,15 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   p.atomic = atomic ? 1 : 0;
   p.act_cols = a.act_cols;
   D2R_CHECK_ARG(a.act_cols % 8 == 0, "gemm: act_cols must be a multiple of 8");
+  if (atomic) {
+    p.variant = EV_ATOMIC;
+  } else if (a.epilogue == D2R_EPI_SQDIFF) {
+    D2R_CHECK_ARG(a.r_dtype == a.c_dtype, "gemm: SQDIFF needs residual and outputs of the same dtype");
+    p.variant = a.c_dtype == D2R_BF16 ? EV_SQ_BF16 : EV_SQ_F32;
+  } else {
+    const int base = a.c_dtype == D2R_BF16 ? EV_BF16 : EV_F32;
+    p.variant = base + (a.residual ? (a.r_dtype == D2R_BF16 ? 2 : 1) : 0);
+  }
 
   if (p.split_k > 1 && !a.accumulate) {
     // split-K partial sums are combined with atomics: C must start at zero (dense C only)

@@ -106,7 +106,7 @@ def _split_k(m_out: int, n_out: int, k: int, tc: bool) -> int:
     else:
         tiles = ((m_out + 63) // 64) * ((n_out + 63) // 64)
         kb = (k + 15) // 16
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    want = max(1, (2 * 148) // tiles)      # <= 2 full waves of 148 SMs
     return max(1, min(want, kb, 64))
 
 
@@ -162,10 +162,33 @@ def _row0_bwd(env: Env, d_vec: Tensor, y_vec: Tensor, xfull: Tensor, name: str, 
     K.gemm(dzc, W, dx_full, m=B, n=D, k=D, lda=D, ldb=D, ldc=Ln * D, b_mn=True, residual=dx_full, ldr=Ln * D)
 
 
-def _lin32_bwd(env: Env, dy: Tensor, x: Tensor, name: str, *, y: Optional[Tensor] = None, act: int = L.ACT_NONE,
-               residual: Optional[Tensor] = None) -> Tensor:
-    """fp32 master-weight linear backward for the tiny [B,D] global branches."""
-    return lin_bwd(env, dy, x, x.shape[-1], env.Wf32(name), [name], y=y, act=act, residual=residual)
+def _small_fwd(env: Env, x32: Tensor, name: str, act: int = L.ACT_NONE):
+    """y = act(x W^T + b) for the tiny fp32 [B,D] vectors of the global branches.  bf16 mode: operands are cast
+    and the product runs on tensor cores (fp32 accumulate / output); fp32 mode: CUDA-core GEMM on the masters.
+    Returns (y fp32, x in the GEMM operand dtype -- kept for the weight gradient)."""
+    if env.cd == torch.float32:
+        return K.linear(x32, env.Wf32(name), env.b(name), act=act), x32
+    xc = K.cast(x32, env.cd)
+    return K.linear(xc, env.W(name), env.b(name), act=act, out_dtype=torch.float32), xc
+
+
+def _small_bwd(env: Env, dy32: Tensor, xc: Tensor, name: str, *, y: Optional[Tensor] = None,
+               act: int = L.ACT_NONE) -> Tensor:
+    """-> dx fp32 [B,K]."""
+    dz, db = K.bias_act_bwd(dy32, y, act, True, True)
+    env.grad(name + ".bias", db)
+    tc = env.cd == torch.bfloat16
+    dzc = K.cast(dz, env.cd) if tc else dz
+    W = env.W(name) if tc else env.Wf32(name)
+    N, Kd = W.shape
+    M = dy32.numel() // N
+    dW = torch.empty(N, Kd, device=W.device, dtype=torch.float32)
+    K.gemm(dzc, xc, dW, m=N, n=Kd, k=M, lda=N, ldb=Kd, ldc=Kd, a_mn=True, b_mn=True,
+           split_k=1 if tc else _split_k(N, Kd, M, False))
+    env.grad(name + ".weight", dW)
+    dx = torch.empty(M, Kd, device=W.device, dtype=torch.float32)
+    K.gemm(dzc, W, dx, m=M, n=Kd, k=N, lda=N, ldb=Kd, ldc=Kd, b_mn=True)
+    return dx
 
 
 # ----------------------------------------------------------------------------- attention core
@@ -285,9 +308,9 @@ def _glac_fwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int):
     i0 = _row0_fwd(env, z, c + ".image_cls_pool.dense")
     dg = K.axpby(t0, i0, 1.0, -1.0)
     sq = K.mul(dg, dg)
-    g1 = K.linear(sq, env.Wf32(c + ".fc_sim_tranglo"), env.b(c + ".fc_sim_tranglo"))
+    g1, sq_c = _small_fwd(env, sq, c + ".fc_sim_tranglo")
     ng, rng = K.l2norm_fwd(g1)
-    sg = K.linear(ng, env.Wf32(c + ".fc_2"), env.b(c + ".fc_2"))               # sim_global [B,D]
+    sg, ng_c = _small_fwd(env, ng, c + ".fc_2")                                # sim_global [B,D]
     sgc = sg if env.cd == torch.float32 else K.cast(sg, env.cd)
     s = c + ".SAF_module"
     P = env.P
@@ -295,8 +318,8 @@ def _glac_fwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int):
     out, saf = K.saf_fwd(sgc, t2, P[s + ".attn_sim_w.weight"].detach().view(-1), P[s + ".attn_sim_w.bias"].detach(),
                          P[s + ".bn.weight"].detach(), P[s + ".bn.bias"].detach(), P[s + ".bn.running_mean"],
                          P[s + ".bn.running_var"], nbt, env.training)
-    saved = dict(cma=cma, d1=d1, sl=sl, n1=n1, rn1=rn1, t2=t2, t0=t0, i0=i0, dg=dg, sq=sq, ng=ng, rng=rng, sgc=sgc,
-                 saf=saf)
+    saved = dict(cma=cma, d1=d1, sl=sl, n1=n1, rn1=rn1, t2=t2, t0=t0, i0=i0, dg=dg, sq_c=sq_c, ng=ng, ng_c=ng_c,
+                 rng=rng, sgc=sgc, saf=saf)
     return out, saved
 
 
@@ -324,9 +347,9 @@ def _glac_bwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int, sv, d_ou
     dx = _cma_bwd(env, c + ".CrossModalAlignment", x, kv, ki, sv["cma"], g.view(B, Lq, D), -1.0, gx)
     # global branch
     dsg = d_sgc if env.cd == torch.float32 else K.cast(d_sgc, torch.float32)
-    dng = _lin32_bwd(env, dsg, sv["ng"], c + ".fc_2")
+    dng = _small_bwd(env, dsg, sv["ng_c"], c + ".fc_2")
     dg1 = K.l2norm_bwd(sv["ng"], dng, sv["rng"])
-    dsq = _lin32_bwd(env, dg1, sv["sq"], c + ".fc_sim_tranglo")
+    dsq = _small_bwd(env, dg1, sv["sq_c"], c + ".fc_sim_tranglo")
     ddg = K.mul(dsq, sv["dg"], 2.0)
     _row0_bwd(env, ddg, sv["t0"], x, c + ".text_cls_pool.dense", dx)
     nddg = K.axpby(ddg, None, -1.0, 0.0)
@@ -423,17 +446,17 @@ def _gesc_fwd(env: Env, c: str, x: Tensor, z: Tensor):
     t = _row0_fwd(env, x, c + ".text_cls_pool.dense")
     i = _row0_fwd(env, z, c + ".image_cls_pool.dense")
     u = K.axpby(t, i, 1.0, 1.0)
-    h1 = K.linear(u, env.Wf32(c + ".fc_mlp.0"), env.b(c + ".fc_mlp.0"), act=L.ACT_TANH)
-    gl = K.linear(h1, env.Wf32(c + ".fc_mlp.2"), env.b(c + ".fc_mlp.2"))
+    h1, u_c = _small_fwd(env, u, c + ".fc_mlp.0", L.ACT_TANH)
+    gl, h1_c = _small_fwd(env, h1, c + ".fc_mlp.2")
     g, out = K.gate_fuse_fwd(gl, t, i)
-    return out, dict(t=t, i=i, u=u, h1=h1, g=g)
+    return out, dict(t=t, i=i, u_c=u_c, h1=h1, h1_c=h1_c, g=g)
 
 
 def _gesc_bwd(env: Env, c: str, x: Tensor, z: Tensor, sv, d_out: Tensor, dx_row0: Tensor, dz_row0: Tensor) -> None:
     """d_out fp32 [B,D]; both pooler gradients are accumulated into row 0 of dx_row0 / dz_row0."""
     d_gl, d_t, d_i = K.gate_fuse_bwd(d_out, sv["g"], sv["t"], sv["i"])
-    dh1 = _lin32_bwd(env, d_gl, sv["h1"], c + ".fc_mlp.2")
-    du = _lin32_bwd(env, dh1, sv["u"], c + ".fc_mlp.0", y=sv["h1"], act=L.ACT_TANH)
+    dh1 = _small_bwd(env, d_gl, sv["h1_c"], c + ".fc_mlp.2")
+    du = _small_bwd(env, dh1, sv["u_c"], c + ".fc_mlp.0", y=sv["h1"], act=L.ACT_TANH)
     d_t = K.axpby(d_t, du, 1.0, 1.0)
     d_i = K.axpby(d_i, du, 1.0, 1.0)
     _row0_bwd(env, d_t, sv["t"], x, c + ".text_cls_pool.dense", dx_row0)
@@ -442,45 +465,47 @@ def _gesc_bwd(env: Env, c: str, x: Tensor, z: Tensor, sv, d_out: Tensor, dx_row0
 
 # ----------------------------------------------------------------------------- routers
 def _routers_fwd(env: Env, routers: Sequence[str], pooled: Tensor, n_out: int, final: bool):
-    """routers: prefixes of the K Router modules; pooled fp32 [K,B,D] ([1,B,D] for a shared input)."""
+    """routers: prefixes of the K Router modules; pooled fp32 [K,B,D] ([1,B,D] for a shared input).
+    Hidden layers of all K routers run as ONE batched GEMM (stacked staged weights) in bf16 mode."""
     Kc = len(routers)
+    shared = pooled.shape[0] == 1
     B, D = pooled.shape[1:]
     Hd = env.P[f"{routers[0]}.mlp.0.weight"].shape[0]
     hid = torch.empty(Kc, B, Hd, device=pooled.device, dtype=torch.float32)
-    for j, rn in enumerate(routers):
-        r = f"{rn}.mlp.0"
-        K.linear(pooled[j if pooled.shape[0] > 1 else 0], env.Wf32(r), env.b(r), act=L.ACT_RELU, out=hid[j])
+    names = [f"{rn}.mlp.0" for rn in routers]
+    pooled_c = pooled if env.cd == torch.float32 else K.cast(pooled, env.cd)
+    K.gemm(pooled_c, env.W(*names), hid, m=B, n=Hd, k=D, lda=D, ldb=D, ldc=Hd, batch=Kc,
+           a_str=(0 if shared else B * D, 0), b_str=(Hd * D, 0), c_str=(B * Hd, 0), bias=env.b(*names),
+           bias_sz=Hd, act=L.ACT_RELU)
     w2 = [env.Wf32(f"{rn}.mlp.2") for rn in routers]
     b2 = [env.b(f"{rn}.mlp.2") for rn in routers]
     raw, norm, gate = K.router_head_fwd(hid, w2, b2, n_out, final)
-    return norm, gate, dict(pooled=pooled, hid=hid, raw=raw, w2=w2)
+    return norm, gate, dict(pooled=pooled, pooled_c=pooled_c, hid=hid, raw=raw, w2=w2)
 
 
 def _routers_bwd(env: Env, routers: Sequence[str], sv, d_norm: Tensor, final: bool) -> Tensor:
     """-> d_pooled fp32 [K,B,D] (or the sum over cells, [1,B,D], for a shared input)."""
-    pooled, hid = sv["pooled"], sv["hid"]
+    pooled, pooled_c, hid = sv["pooled"], sv["pooled_c"], sv["hid"]
     Kc, B, Hd = hid.shape
     D = pooled.shape[2]
     shared = pooled.shape[0] == 1
     d_hid, _, d_w2, d_b2 = K.router_head_bwd(d_norm.contiguous(), sv["raw"], hid, sv["w2"], final)
-    d_pooled = torch.empty(1 if shared else Kc, B, D, device=hid.device, dtype=torch.float32)
+    names = [f"{rn}.mlp.0" for rn in routers]
     for j, r in enumerate(routers):
         env.grad(r + ".mlp.2.weight", d_w2[j])
         env.grad(r + ".mlp.2.bias", d_b2[j])
-        W1 = env.Wf32(r + ".mlp.0")
-        x = pooled[0 if shared else j]
-        # d_hid already carries the hidden ReLU mask
-        dz = d_hid[j]
-        dW = torch.empty_like(W1)
-        K.gemm(dz, x, dW, m=Hd, n=D, k=B, lda=Hd, ldb=D, ldc=D, a_mn=True, b_mn=True,
-               split_k=_split_k(Hd, D, B, False))
-        _, db = K.bias_act_bwd(dz, None, L.ACT_NONE, False, True)
-        env.grad(r + ".mlp.0.weight", dW)
-        env.grad(r + ".mlp.0.bias", db)
-        dst = d_pooled[0 if shared else j]
-        acc = shared and j > 0
-        K.gemm(dz, W1, dst, m=B, n=D, k=Hd, lda=Hd, ldb=D, ldc=D, b_mn=True, residual=dst if acc else None,
-               ldr=D if acc else 0)
+        _, db = K.bias_act_bwd(d_hid[j], None, L.ACT_NONE, False, True)    # d_hid carries the ReLU mask
+        env.grad(names[j] + ".bias", db)
+    dzc = d_hid if env.cd == torch.float32 else K.cast(d_hid, env.cd)       # [K,B,Hd]
+    dW = torch.empty(Kc, Hd, D, device=hid.device, dtype=torch.float32)
+    K.gemm(dzc, pooled_c, dW, m=Hd, n=D, k=B, lda=Hd, ldb=D, ldc=D, a_mn=True, b_mn=True, batch=Kc,
+           a_str=(B * Hd, 0), b_str=(0 if shared else B * D, 0), c_str=(Hd * D, 0))
+    for j, nme in enumerate(names):
+        env.grad(nme + ".weight", dW[j])
+    d_pooled = (torch.zeros if shared else torch.empty)(1 if shared else Kc, B, D, device=hid.device,
+                                                        dtype=torch.float32)
+    K.gemm(dzc, env.W(*names), d_pooled, m=B, n=D, k=Hd, lda=Hd, ldb=D, ldc=D, b_mn=True, batch=Kc,
+           a_str=(B * Hd, 0), b_str=(Hd * D, 0), c_str=(0 if shared else B * D, 0), accumulate=shared)
     return d_pooled
 
 

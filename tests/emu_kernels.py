@@ -54,7 +54,9 @@ def gemm(a, b, c, *, m, n, k, lda, ldb, ldc, a_mn=False, b_mn=False, batch=1, ba
         if R is not None:
             v = v + R
     if accumulate:
-        C.add_(v.to(c.dtype))
+        for zo in range(bo):           # batches may alias the same C (atomic accumulation on the GPU)
+            for zi in range(bi):
+                C[zo, zi].add_(v[zo, zi].to(c.dtype))
     else:
         C.copy_(v.to(c.dtype))
     return c

@@ -1,0 +1,144 @@
+"""CPU-side checks of the drop-in boundary: class names, constructor signatures, state_dict
+keys / shapes / order and seeded initial values identical to the unmodified reference (fingerprint recorded by
+tests/golden/make_init_fingerprint.py), error behaviour without CUDA, and the data-parallel plan."""
+import argparse
+import inspect
+import json
+import os
+
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_args():
+    return argparse.Namespace(embed_size=768, hid_router=768, hid_IMRC=768, num_head_IMRC=16,
+                              raw_feature_norm_CMRC="clipped_l2norm", lambda_softmax_CMRC=4.0, alpha=0, margin=0.1,
+                              bert_name="bert-base-uncased", vit_name="clip-vit-base-patch32")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    from d2r_b200 import build
+    build.build()
+
+
+@pytest.mark.parametrize("branch", ["text", "image"])
+def test_state_dict_and_seeded_init_match_reference(branch):
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule
+    fp = json.load(open(os.path.join(GOLD, "init_fingerprint.json")))[branch]
+    torch.manual_seed(2023)
+    m = (InteractionModule if branch == "text" else Reversed_InteractionModule)(make_args(), 3, 6, 128)
+    sd = m.state_dict()
+    assert list(sd.keys()) == fp["keys"]
+    assert [list(v.shape) for v in sd.values()] == fp["shapes"]
+    assert [n for n, _ in m.named_parameters()] == fp["params"]
+    for k, v, s, a in zip(sd.keys(), sd.values(), fp["sum"], fp["abssum"]):
+        assert abs(float(v.double().sum()) - s) <= 1e-9 * max(1.0, a), k
+        assert abs(float(v.double().abs().sum()) - a) <= 1e-9 * max(1.0, a), k
+
+
+def test_signatures_match_reference():
+    from d2r_b200.interaction import Cells, DynamicInteraction, InteractionModule, Refinement, Router, SelfAttention, XModules
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(InteractionModule.InteractionModule.__init__) == ["self", "args", "num_layer_routing", "num_cells", "path_hid"]
+    assert sig(InteractionModule.InteractionModule.forward)[:3] == ["self", "text", "image"]
+    assert sig(InteractionModule.Reversed_InteractionModule.forward)[:3] == ["self", "text", "image"]
+    for cls in ("DynamicInteraction_Layer0", "DynamicInteraction_Layer", "Reversed_DynamicInteraction_Layer0",
+                "Reversed_DynamicInteraction_Layer"):
+        assert sig(getattr(DynamicInteraction, cls).__init__) == ["self", "args", "num_cell", "num_out_path"]
+    assert sig(DynamicInteraction.DynamicInteraction_Layer0.forward) == ["self", "text", "image"]
+    assert sig(DynamicInteraction.DynamicInteraction_Layer.forward) == ["self", "ref_wrd", "text", "image"]
+    for cls in ("RectifiedIdentityCell", "IntraModelReasoningCell", "CrossModalRefinementCell",
+                "GlobalLocalAlignmentCell", "GlobalEnhancedSemanticCell", "ContextRichCrossModalCell"):
+        assert sig(getattr(Cells, cls).__init__) == ["self", "args", "num_out_path"]
+    assert sig(Router.Router.__init__) == ["self", "num_out_path", "embed_size", "hid"]
+    assert sig(SelfAttention.SelfAttention.__init__) == ["self", "embed_size", "hid_size", "h", "drop"]
+    assert sig(Refinement.Refinement.__init__) == ["self", "args", "embed_size", "raw_feature_norm", "lambda_softmax"]
+    assert sig(XModules.CrossModalAlignment.__init__) == ["self", "config", "args"]
+    assert sig(XModules.AttentionFiltration.__init__) == ["self", "sim_dim"]
+
+
+def test_envelope_errors():
+    from d2r_b200.interaction import InteractionModule
+    with pytest.raises(ValueError):
+        InteractionModule(make_args(), 3, 5, 128)        # only 4 or 6 cells exist
+    with pytest.raises(ValueError):
+        InteractionModule(make_args(), 1, 6, 128)
+    m = InteractionModule(make_args(), 2, 4, 128)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.randn(2, 4, 768), torch.randn(2, 3, 768))
+
+
+def test_dead_parameter_plan_matches_reference_fixture():
+    import numpy as np
+    from d2r_b200 import dp
+    gold = np.load(os.path.join(GOLD, "text_r3_train.npz"))
+    dead = set(gold["dead"].tolist())
+    fp = json.load(open(os.path.join(GOLD, "init_fingerprint.json")))["text"]
+    for n in fp["params"]:
+        assert dp.is_live(n) == (n not in dead), n
+
+
+def test_shard_batch():
+    from d2r_b200.dp import shard_batch
+    for n, w in [(256, 8), (10, 4), (7, 2), (3, 8)]:
+        spans = [shard_batch(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from d2r_b200.dp import GradAllReducer, shard_batch
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+
+    class Tiny(torch.nn.Module):           # names mimic live and dead stack parameters
+        def __init__(self):
+            super().__init__()
+            self.live = torch.nn.Linear(6, 3)
+            self.path_mapping = torch.nn.Linear(3, 2)     # dead: never used in forward
+
+        def forward(self, x):
+            return self.live(x)
+
+    m = Tiny()
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    lo, hi = shard_batch(8, rank, world)
+    m(x[lo:hi]).pow(2).mean().backward()
+    red = GradAllReducer([m])
+    assert red.names == ["0.live.weight", "0.live.bias"]
+    red.step()
+    q.put((rank, m.live.weight.grad.clone(), m.live.bias.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_allreduce_gloo_world2():
+    """N-rank DP == mean of the per-shard gradients (world_size 2, gloo, CPU)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(6, 3)
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    gs = []
+    for lo, hi in ((0, 4), (4, 8)):
+        lin.zero_grad()
+        lin(x[lo:hi]).pow(2).mean().backward()
+        gs.append(lin.weight.grad.clone())
+    torch.testing.assert_close(res[0][1], (gs[0] + gs[1]) / 2)
