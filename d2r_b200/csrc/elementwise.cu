@@ -63,19 +63,31 @@ __global__ void __launch_bounds__(kThreads) bias_act_bwd_kernel(const T* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (col < cols) {
-    for (long long r = r0 + warp; r < r1; r += 8) {
-      float g[8];
-      load8(dy + r * ld + col, g);
-      if (act != D2R_ACT_NONE) {
-        float yv[8];
-        load8(y + r * ld + col, yv);
+    // 4 independent rows per iteration keep 4-8 16-byte loads in flight per thread
+    for (long long rb = r0 + warp * 4; rb < r1; rb += 32) {
+      float g[4][8], yv[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          g[j] = act == D2R_ACT_RELU ? (yv[j] > 0.f ? g[j] : 0.f) : g[j] * (1.f - yv[j] * yv[j]);
+      for (int u = 0; u < 4; ++u) {
+        const long long r = rb + u;
+        if (r < r1) {
+          load8(dy + r * ld + col, g[u]);
+          if (act != D2R_ACT_NONE) load8(y + r * ld + col, yv[u]);
+        }
       }
-      if (dz) store8(dz + r * ld + col, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+      for (int u = 0; u < 4; ++u) {
+        const long long r = rb + u;
+        if (r < r1) {
+          if (act != D2R_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              g[u][j] = act == D2R_ACT_RELU ? (yv[u][j] > 0.f ? g[u][j] : 0.f) : g[u][j] * (1.f - yv[u][j] * yv[u][j]);
+            if (dz) store8(dz + r * ld + col, g[u]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += g[u][j];
+        }
+      }
     }
   }
   if (db) {

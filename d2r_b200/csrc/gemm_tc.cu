@@ -5,7 +5,7 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor.4d -> 128B-swizzled smem ring)
 //   warp 1      MMA issuer     (one thread: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> bias/act/residual -> global)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b -> registers -> bias/act/residual -> global)
 // Accumulators are double-buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i
 // overlaps the main loop of tile i+1.  Operands may be K-major or MN-major (transposed) so the
 // same kernel serves forward (x W^T), data-gradient (dy W) and weight-gradient (dy^T x).
@@ -23,6 +23,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
+constexpr int kTcThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ATOM_BYTES = 64 * BK * 2;   // one [64 x 64] bf16 swizzle tile = 8 KB
 
@@ -33,7 +34,7 @@ struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BIAS_BYTES = 4 * BN * 4;
+  static constexpr int BIAS_BYTES = 8 * BN * 4;   // one private bias slice per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
@@ -107,15 +108,55 @@ __device__ __forceinline__ void ld_group(const T* ptr, float (&v)[8], int nvalid
   }
 }
 
+// Register image of one row's 32 residual values (fetched ahead of the TMEM wait so the global-load
+// latency overlaps the accumulator read instead of sitting on the critical path of every 8 columns).
+template <typename RT> struct ResRegs { float v[32]; };
+template <> struct ResRegs<NoRes> {};
+template <> struct ResRegs<__nv_bfloat16> { uint4 v[4]; };
+template <> struct ResRegs<float> { float4 v[8]; };
+
+template <typename RT>
+__device__ __forceinline__ void prefetch_res(ResRegs<RT>& pre, const RT* rrow, int col0) {
+  if constexpr (!std::is_same<RT, NoRes>::value) {
+    constexpr int NV = 32 / (16 / sizeof(RT));        // 16-byte vectors per 32 elements
+    using Vec = typename std::remove_reference<decltype(pre.v[0])>::type;
+    const Vec* ptr = reinterpret_cast<const Vec*>(rrow + col0);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pre.v[i] = ptr[i];
+  }
+}
+
+template <typename RT>
+__device__ __forceinline__ void unpack_group(const ResRegs<RT>& pre, int g, float (&res)[8]) {
+  if constexpr (std::is_same<RT, __nv_bfloat16>::value) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pre.v[g]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      res[2 * i] = f.x;
+      res[2 * i + 1] = f.y;
+    }
+  } else if constexpr (std::is_same<RT, float>::value) {
+    const float4 a = pre.v[2 * g], b = pre.v[2 * g + 1];
+    res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
+    res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+  }
+}
+
 // one thread: 32 consecutive accumulator columns (col0 .. col0+31) of one output row
-template <typename CT, typename RT, int MODE>
+// FAST: the tile lies fully inside the matrix and every row pointer is 16-byte aligned -> no bounds or
+// alignment tests in the instruction stream (the epilogue warps are issue-bound, not memory-bound).
+template <typename CT, typename RT, int MODE, bool FAST>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&r)[32], const float* sbias,
-                                               CT* crow, CT* c2row, const RT* rrow, int col0) {
+                                               CT* crow, CT* c2row, const ResRegs<RT>& pre, const RT* rrow,
+                                               int col0) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int col = col0 + g * 8;
-    if (col >= p.n) break;
-    const int nvalid = min(8, p.n - col);
+    if constexpr (!FAST) {
+      if (col >= p.n) break;
+    }
+    const int nvalid = FAST ? 8 : min(8, p.n - col);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(r[g * 8 + i]);
@@ -126,19 +167,36 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
       v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
     if constexpr (MODE == 2) {
+      float* dst = reinterpret_cast<float*>(crow) + col;
+      if (FAST || (nvalid == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        // red.global.add.v4.f32: one L2 reduction per 16 bytes instead of per element
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                     "f"(v[3])
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
+                     "f"(v[6]), "f"(v[7])
+                     : "memory");
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nvalid) atomicAdd(reinterpret_cast<float*>(crow) + col + i, v[i]);
+        for (int i = 0; i < 8; ++i)
+          if (i < nvalid) atomicAdd(dst + i, v[i]);
+      }
     } else if constexpr (MODE == 1) {
       float res[8], d[8];
-      ld_group(rrow + col, res, nvalid);
+      if constexpr (FAST) unpack_group(pre, g, res);
+      else ld_group(rrow + col, res, nvalid);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         d[i] = res[i] - v[i];
         v[i] = d[i] * d[i];
       }
-      st_group(c2row + col, d, nvalid);
-      st_group(crow + col, v, nvalid);
+      if constexpr (FAST) {
+        store8(c2row + col, d);
+        store8(crow + col, v);
+      } else {
+        st_group(c2row + col, d, nvalid);
+        st_group(crow + col, v, nvalid);
+      }
     } else {
       if (p.act != D2R_ACT_NONE && (p.act_cols == 0 || col < p.act_cols)) {
         if (p.act == D2R_ACT_RELU) {
@@ -151,18 +209,40 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
       }
       if constexpr (!std::is_same<RT, NoRes>::value) {
         float res[8];
-        ld_group(rrow + col, res, nvalid);
+        if constexpr (FAST) unpack_group(pre, g, res);
+        else ld_group(rrow + col, res, nvalid);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += res[i];
       }
-      st_group(crow + col, v, nvalid);
+      if constexpr (FAST) store8(crow + col, v);
+      else st_group(crow + col, v, nvalid);
     }
   }
 }
 
+// chunks [cb, ce) of one accumulator tile.  Latency of the TMEM load / residual fetch is hidden by the
+// sibling epilogue warp on the same scheduler (two warps per SMSP), so a single register buffer suffices.
+template <typename CT, typename RT, int MODE, bool FAST>
+__device__ __forceinline__ void epilogue_chunks(const TcParams& p, uint32_t taddr, const float* sbias_tile, CT* crow,
+                                                CT* c2row, const RT* rrow, int n0, int cb, int ce, bool row_ok) {
+#pragma unroll 1
+  for (int c = cb; c < ce; ++c) {
+    uint32_t ra[32];
+    ResRegs<RT> pa;
+    tmem_ld32(taddr + c * 32, ra);
+    if (FAST && row_ok) prefetch_res<RT>(pa, rrow, n0 + c * 32);
+    tmem_ld_wait();
+    if (row_ok)
+      epilogue_chunk<CT, RT, MODE, FAST>(p, ra, sbias_tile ? sbias_tile + c * 32 : nullptr, crow, c2row, pa, rrow,
+                                         n0 + c * 32);
+  }
+}
+
+// 8 epilogue warps: warp pair (q, half) shares TMEM lane quarter q; half 0 takes the first half of the
+// tile's 32-column chunks, half 1 the second (two warps per scheduler hide each other's stalls).
 template <int BN, typename CT, typename RT, int MODE>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, float* sbias_warp, int q, int lane) {
+                                              uint64_t* tmem_empty, float* sbias_warp, int q, int half, int lane) {
   int acc = 0;
   uint32_t acc_phase = 0;
   for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -187,23 +267,18 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
              static_cast<long long>(tc.zi) * p.r_si + row * p.ldr;
     const int ncols = min(BN, p.n - tc.n0);
     const int nchunks = (ncols + 31) >> 5;
+    const int cmid = (nchunks + 1) >> 1;
+    const int cb = half == 0 ? 0 : cmid;
+    const int ce = half == 0 ? cmid : nchunks;
     const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t ra[32], rb[32];
-    tmem_ld32(taddr, ra);
-#pragma unroll 1
-    for (int c = 0; c < nchunks; c += 2) {
-      tmem_ld_wait();
-      if (c + 1 < nchunks) tmem_ld32(taddr + (c + 1) * 32, rb);
-      if (row_ok)
-        epilogue_chunk<CT, RT, MODE>(p, ra, p.bias ? sbias_warp + c * 32 : nullptr, crow, c2row, rrow, tc.n0 + c * 32);
-      if (c + 1 < nchunks) {
-        tmem_ld_wait();
-        if (c + 2 < nchunks) tmem_ld32(taddr + (c + 2) * 32, ra);
-        if (row_ok)
-          epilogue_chunk<CT, RT, MODE>(p, rb, p.bias ? sbias_warp + (c + 1) * 32 : nullptr, crow, c2row, rrow,
-                                       tc.n0 + (c + 1) * 32);
-      }
-    }
+    const float* sb = p.bias ? sbias_warp : nullptr;
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(c2row) |
+                          reinterpret_cast<uintptr_t>(rrow)) & 15) == 0;
+    const bool fast = (tc.n0 + BN <= p.n) && __all_sync(0xffffffffu, ptr_ok || !row_ok);
+    if (fast)
+      epilogue_chunks<CT, RT, MODE, true>(p, taddr, sb, crow, c2row, rrow, tc.n0, cb, ce, row_ok);
+    else
+      epilogue_chunks<CT, RT, MODE, false>(p, taddr, sb, crow, c2row, rrow, tc.n0, cb, ce, row_ok);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -217,7 +292,7 @@ enum EpiVariant {
 };
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   using Cfg = TcCfg<BN>;
@@ -244,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 8);
     }
     fence_barrier_init();
   }
@@ -338,17 +413,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------- epilogue (4 warps)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     float* sb = sbias + (warp - 2) * BN;
+    const int half = (warp - 2) >> 2;
     using bf16 = __nv_bfloat16;
     switch (p.variant) {
-      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
-      default:            epilogue_loop<BN, float, NoRes, 2>(p, tmem_base, tmem_full, tmem_empty, sb, q, lane); break;
+      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      default:            epilogue_loop<BN, float, NoRes, 2>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
     }
   }
 
@@ -409,7 +485,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
     attr_set = true;
   }
   long long grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<(unsigned)grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<(unsigned)grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }

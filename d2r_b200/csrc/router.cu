@@ -151,29 +151,36 @@ __global__ void __launch_bounds__(kThreads) router_head_bwd_kernel(const float* 
   }
 }
 
-// block per (cell j, out path i): dW2_j[i,:] += sum_b d_logit[b,i,j] hid[j,b,:];  db2_j[i] += sum_b d_logit
+// grid (K*n_out, H/64): block = 64 columns x 4 batch groups.  dW2_j[i,:] += sum_b d_logit[b,i,j] hid[j,b,:];
+// db2_j[i] += sum_b d_logit[b,i,j]
 __global__ void __launch_bounds__(kThreads) router_head_wgrad_kernel(const float* __restrict__ d_logit,
                                                                      const float* __restrict__ hid, int K, int n_out,
                                                                      long long B, int H, d2r_ptr8 d_w2, d2r_ptr8 d_b2) {
-  __shared__ float sm[8];
+  __shared__ float red[4][64];
   const int j = blockIdx.x / n_out, i = blockIdx.x % n_out;
-  float* dw = static_cast<float*>(const_cast<void*>(d_w2.p[j])) + (long long)i * H;
-  float* db = static_cast<float*>(const_cast<void*>(d_b2.p[j])) + i;
-  for (int c = threadIdx.x; c < H; c += kThreads) {
-    float acc = 0.f;
-    for (long long b = 0; b < B; ++b)
-      acc += d_logit[(b * n_out + i) * K + j] * hid[((long long)j * B + b) * H + c];
-    dw[c] += acc;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + tx;
+  float acc = 0.f, sb = 0.f;
+  if (c < H) {
+#pragma unroll 4
+    for (long long b = ty; b < B; b += 4) {
+      const float dl = d_logit[(b * n_out + i) * K + j];
+      acc = fmaf(dl, hid[((long long)j * B + b) * H + c], acc);
+      sb += dl;
+    }
   }
-  float s = 0.f;
-  for (long long b = threadIdx.x; b < B; b += kThreads) s += d_logit[(b * n_out + i) * K + j];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  red[ty][tx] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += sm[w];
-    *db += t;
+  if (ty == 0 && c < H) {
+    float* dw = static_cast<float*>(const_cast<void*>(d_w2.p[j])) + (long long)i * H;
+    dw[c] += red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx];
+  }
+  __syncthreads();
+  if (blockIdx.y == 0 && tx == 0) red[ty][0] = sb;
+  __syncthreads();
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    float* db = static_cast<float*>(const_cast<void*>(d_b2.p[j])) + i;
+    *db += red[0][0] + red[1][0] + red[2][0] + red[3][0];
   }
 }
 
@@ -222,7 +229,8 @@ int d2r_router_head_bwd(const float* d_norm, const float* raw, const float* hid,
   D2R_CHECK_ARG(K >= 1 && K <= 8 && n_out >= 1 && n_out <= 8 && B > 0, "router_head_bwd: bad shape");
   router_head_bwd_kernel<<<(unsigned)B, kThreads, 0, st>>>(d_norm, raw, hid, w2, K, n_out, B, H, final_layer, d_hid,
                                                            d_logit);
-  router_head_wgrad_kernel<<<(unsigned)(K * n_out), kThreads, 0, st>>>(d_logit, hid, K, n_out, B, H, d_w2, d_b2);
+  router_head_wgrad_kernel<<<dim3((unsigned)(K * n_out), (unsigned)((H + 63) / 64)), kThreads, 0, st>>>(d_logit, hid, K,
+                                                                                                   n_out, B, H, d_w2, d_b2);
   count_launch(2);
   return check_launch("router_head_bwd_kernel");
 }

@@ -77,7 +77,7 @@ def test_against_reference_golden(case, bf16):
         assert relerr(p, gold[f"probs{li}"]) <= p_tol, ("probs", li, relerr(p, gold[f"probs{li}"]))
     assert relerr(sim, gold["sim"]) <= 2 * p_tol
     # the realistic cases push x20 outlier channels through softmax(3.6 q.k): bf16 is only judged on routing
-    o_tol = (0.25 if realistic else 5e-2) if bf16 else 1e-4
+    o_tol = (0.5 if realistic else 5e-2) if bf16 else 1e-4
     assert relerr(out, gold["out"]) <= o_tol, ("out", relerr(out, gold["out"]))
     if not bf16:
         assert relerr(d_text, gold["d_text"]) <= 2e-3, ("d_text", relerr(d_text, gold["d_text"]))
