@@ -11,6 +11,9 @@
 // same kernel serves forward (x W^T), data-gradient (dy W) and weight-gradient (dy^T x).
 #include <cuda.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -35,7 +38,8 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = 8 * BN * 4;   // one private bias slice per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
+  static constexpr int STORE_BYTES = 8 * 2048;    // one 32-row x 64-byte staging tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
 struct TcParams {
@@ -51,6 +55,8 @@ struct TcParams {
   long long ldc, ldr, c_so, c_si, r_so, r_si, bias_sz;
   float alpha;
   int act, epilogue, c_dtype, r_dtype, atomic, act_cols, variant;
+  int tma_store;   // 1: C (and c2) are written with TMA bulk tensor stores through a smem staging tile
+  int debug;   // D2R_TC_DEBUG env (bring-up only): 1 = skip epilogue stores, 2 = skip the epilogue body
 };
 
 struct TileCoord {
@@ -75,237 +81,24 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long t,
   return tc;
 }
 
-// ------------------------------------------------------------------ epilogue
-// Variants are compiled as separate straight-line loops (one dispatch per kernel) so that the hot
-// loop stays small enough for the instruction cache; MODE 0 = bias/act/residual, 1 = squared
-// difference (two outputs), 2 = fp32 atomic accumulation (split-K / accumulate).
-struct NoRes {};
-
-__device__ __forceinline__ float fast_tanh(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-template <typename T>
-__device__ __forceinline__ void st_group(T* ptr, const float (&v)[8], int nvalid) {
-  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
-    store8(ptr, v);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nvalid) Elem<T>::st(ptr + i, v[i]);
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void ld_group(const T* ptr, float (&v)[8], int nvalid) {
-  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
-    load8(ptr, v);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (i < nvalid) ? Elem<T>::ld(ptr + i) : 0.f;
-  }
-}
-
-// Register image of one row's 32 residual values (fetched ahead of the TMEM wait so the global-load
-// latency overlaps the accumulator read instead of sitting on the critical path of every 8 columns).
-template <typename RT> struct ResRegs { float v[32]; };
-template <> struct ResRegs<NoRes> {};
-template <> struct ResRegs<__nv_bfloat16> { uint4 v[4]; };
-template <> struct ResRegs<float> { float4 v[8]; };
-
-template <typename RT>
-__device__ __forceinline__ void prefetch_res(ResRegs<RT>& pre, const RT* rrow, int col0) {
-  if constexpr (!std::is_same<RT, NoRes>::value) {
-    constexpr int NV = 32 / (16 / sizeof(RT));        // 16-byte vectors per 32 elements
-    using Vec = typename std::remove_reference<decltype(pre.v[0])>::type;
-    const Vec* ptr = reinterpret_cast<const Vec*>(rrow + col0);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) pre.v[i] = ptr[i];
-  }
-}
-
-template <typename RT>
-__device__ __forceinline__ void unpack_group(const ResRegs<RT>& pre, int g, float (&res)[8]) {
-  if constexpr (std::is_same<RT, __nv_bfloat16>::value) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pre.v[g]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      res[2 * i] = f.x;
-      res[2 * i + 1] = f.y;
-    }
-  } else if constexpr (std::is_same<RT, float>::value) {
-    const float4 a = pre.v[2 * g], b = pre.v[2 * g + 1];
-    res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
-    res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
-  }
-}
-
-// one thread: 32 consecutive accumulator columns (col0 .. col0+31) of one output row
-// FAST: the tile lies fully inside the matrix and every row pointer is 16-byte aligned -> no bounds or
-// alignment tests in the instruction stream (the epilogue warps are issue-bound, not memory-bound).
-template <typename CT, typename RT, int MODE, bool FAST>
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&r)[32], const float* sbias,
-                                               CT* crow, CT* c2row, const ResRegs<RT>& pre, const RT* rrow,
-                                               int col0) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int col = col0 + g * 8;
-    if constexpr (!FAST) {
-      if (col >= p.n) break;
-    }
-    const int nvalid = FAST ? 8 : min(8, p.n - col);
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(r[g * 8 + i]);
-    if (sbias) {
-      const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
-    if constexpr (MODE == 2) {
-      float* dst = reinterpret_cast<float*>(crow) + col;
-      if (FAST || (nvalid == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-        // red.global.add.v4.f32: one L2 reduction per 16 bytes instead of per element
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                     "f"(v[3])
-                     : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
-                     "f"(v[6]), "f"(v[7])
-                     : "memory");
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < nvalid) atomicAdd(dst + i, v[i]);
-      }
-    } else if constexpr (MODE == 1) {
-      float res[8], d[8];
-      if constexpr (FAST) unpack_group(pre, g, res);
-      else ld_group(rrow + col, res, nvalid);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        d[i] = res[i] - v[i];
-        v[i] = d[i] * d[i];
-      }
-      if constexpr (FAST) {
-        store8(c2row + col, d);
-        store8(crow + col, v);
-      } else {
-        st_group(c2row + col, d, nvalid);
-        st_group(crow + col, v, nvalid);
-      }
-    } else {
-      if (p.act != D2R_ACT_NONE && (p.act_cols == 0 || col < p.act_cols)) {
-        if (p.act == D2R_ACT_RELU) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = sizeof(CT) == 2 ? fast_tanh(v[i]) : tanhf(v[i]);
-        }
-      }
-      if constexpr (!std::is_same<RT, NoRes>::value) {
-        float res[8];
-        if constexpr (FAST) unpack_group(pre, g, res);
-        else ld_group(rrow + col, res, nvalid);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += res[i];
-      }
-      if constexpr (FAST) store8(crow + col, v);
-      else st_group(crow + col, v, nvalid);
-    }
-  }
-}
-
-// chunks [cb, ce) of one accumulator tile.  Latency of the TMEM load / residual fetch is hidden by the
-// sibling epilogue warp on the same scheduler (two warps per SMSP), so a single register buffer suffices.
-template <typename CT, typename RT, int MODE, bool FAST>
-__device__ __forceinline__ void epilogue_chunks(const TcParams& p, uint32_t taddr, const float* sbias_tile, CT* crow,
-                                                CT* c2row, const RT* rrow, int n0, int cb, int ce, bool row_ok) {
-#pragma unroll 1
-  for (int c = cb; c < ce; ++c) {
-    uint32_t ra[32];
-    ResRegs<RT> pa;
-    tmem_ld32(taddr + c * 32, ra);
-    if (FAST && row_ok) prefetch_res<RT>(pa, rrow, n0 + c * 32);
-    tmem_ld_wait();
-    if (row_ok)
-      epilogue_chunk<CT, RT, MODE, FAST>(p, ra, sbias_tile ? sbias_tile + c * 32 : nullptr, crow, c2row, pa, rrow,
-                                         n0 + c * 32);
-  }
-}
-
-// 8 epilogue warps: warp pair (q, half) shares TMEM lane quarter q; half 0 takes the first half of the
-// tile's 32-column chunks, half 1 the second (two warps per scheduler hide each other's stalls).
-template <int BN, typename CT, typename RT, int MODE>
-__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, float* sbias_warp, int q, int half, int lane) {
-  int acc = 0;
-  uint32_t acc_phase = 0;
-  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-    const TileCoord tc = decode_tile(p, t, BN);
-    // stage this tile's bias slice in shared memory while the accumulator is still being produced
-    if (p.bias) {
-      const float* bias = p.bias + static_cast<long long>(tc.z) * p.bias_sz;
-      for (int i = lane; i < BN; i += 32) sbias_warp[i] = (tc.n0 + i < p.n) ? __ldg(bias + tc.n0 + i) : 0.f;
-    }
-    __syncwarp();
-    mbar_wait(&tmem_full[acc], acc_phase);
-    tc_fence_after();
-    const long long row = tc.m0 + q * 32 + lane;
-    const bool row_ok = row < p.m;
-    const long long c_off = static_cast<long long>(tc.zo) * p.c_so + static_cast<long long>(tc.zi) * p.c_si +
-                            row * p.ldc;
-    CT* crow = reinterpret_cast<CT*>(p.c) + c_off;
-    CT* c2row = MODE == 1 ? reinterpret_cast<CT*>(p.c2) + c_off : nullptr;
-    const RT* rrow = nullptr;
-    if constexpr (!std::is_same<RT, NoRes>::value)
-      rrow = reinterpret_cast<const RT*>(p.residual) + static_cast<long long>(tc.zo) * p.r_so +
-             static_cast<long long>(tc.zi) * p.r_si + row * p.ldr;
-    const int ncols = min(BN, p.n - tc.n0);
-    const int nchunks = (ncols + 31) >> 5;
-    const int cmid = (nchunks + 1) >> 1;
-    const int cb = half == 0 ? 0 : cmid;
-    const int ce = half == 0 ? cmid : nchunks;
-    const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-    const float* sb = p.bias ? sbias_warp : nullptr;
-    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(c2row) |
-                          reinterpret_cast<uintptr_t>(rrow)) & 15) == 0;
-    const bool fast = (tc.n0 + BN <= p.n) && __all_sync(0xffffffffu, ptr_ok || !row_ok);
-    if (fast)
-      epilogue_chunks<CT, RT, MODE, true>(p, taddr, sb, crow, c2row, rrow, tc.n0, cb, ce, row_ok);
-    else
-      epilogue_chunks<CT, RT, MODE, false>(p, taddr, sb, crow, c2row, rrow, tc.n0, cb, ce, row_ok);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-    acc ^= 1;
-    if (acc == 0) acc_phase ^= 1;
-  }
-}
-
-enum EpiVariant {
-  EV_F32 = 0, EV_F32_RF32, EV_F32_RBF16, EV_BF16, EV_BF16_RF32, EV_BF16_RBF16, EV_SQ_F32, EV_SQ_BF16, EV_ATOMIC
-};
+#include "gemm_tc_epilogue.cuh"
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on a 1024-byte boundary
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* store_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // [8][2048]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* sbias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);   // [4][BN]
+  float* sbias = reinterpret_cast<float*>(store_stage + Cfg::STORE_BYTES + Cfg::BAR_BYTES);   // [8][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -313,6 +106,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tmC);
+      if (p.epilogue == D2R_EPI_SQDIFF) tma_prefetch_desc(&tmC2);
+    }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -414,17 +211,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     float* sb = sbias + (warp - 2) * BN;
     const int half = (warp - 2) >> 2;
+    uint8_t* stg = store_stage + (warp - 2) * 2048;
     using bf16 = __nv_bfloat16;
     switch (p.variant) {
-      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
-      default:            epilogue_loop<BN, float, NoRes, 2>(p, tmem_base, tmem_full, tmem_empty, sb, q, half, lane); break;
+      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      default:            epilogue_loop<BN, float, NoRes, 2>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
     }
   }
 
@@ -455,19 +253,19 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 4-D map {inner (contiguous), rows, batch_inner, batch_outer}; bf16; 128-byte swizzle; OOB -> 0
-int encode_operand(CUtensorMap* tm, const void* base, long long inner, long long rows, long long bi, long long bo,
-                   long long ld, long long si, long long so, int box_rows) {
+int encode_map(CUtensorMap* tm, const void* base, int es, long long inner, long long rows, long long bi, long long bo,
+               long long ld, long long si, long long so, int box_inner, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(D2R_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const long long row_bytes = ld * 2;
+  const long long row_bytes = ld * es;
   cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)bi, (cuuint64_t)bo};
-  cuuint64_t strides[3] = {(cuuint64_t)row_bytes, (cuuint64_t)(bi > 1 ? si * 2 : row_bytes),
-                           (cuuint64_t)(bo > 1 ? so * 2 : row_bytes)};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)row_bytes, (cuuint64_t)(bi > 1 ? si * es : row_bytes),
+                           (cuuint64_t)(bo > 1 ? so * es : row_bytes)};
+  cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(D2R_ERR_CUDA,
                      "cuTensorMapEncodeTiled failed (%d): dims=[%lld,%lld,%lld,%lld] ld=%lld si=%lld so=%lld", (int)r,
@@ -475,8 +273,14 @@ int encode_operand(CUtensorMap* tm, const void* base, long long inner, long long
   return D2R_OK;
 }
 
+int encode_operand(CUtensorMap* tm, const void* base, long long inner, long long rows, long long bi, long long bo,
+                   long long ld, long long si, long long so, int box_rows) {
+  return encode_map(tm, base, 2, inner, rows, bi, bo, ld, si, so, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int BN, bool A_MN, bool B_MN>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+              const TcParams& p, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -485,18 +289,18 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
     attr_set = true;
   }
   long long grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<(unsigned)grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<(unsigned)grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }
 
 template <int BN>
-int launch_tc_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
-                    cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(tmA, tmB, p, stream);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true>(tmA, tmB, p, stream);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false>(tmA, tmB, p, stream);
-  return launch_tc<BN, true, true>(tmA, tmB, p, stream);
+int launch_tc_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                    const CUtensorMap& tmC2, const TcParams& p, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(tmA, tmB, tmC, tmC2, p, stream);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true>(tmA, tmB, tmC, tmC2, p, stream);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false>(tmA, tmB, tmC, tmC2, p, stream);
+  return launch_tc<BN, true, true>(tmA, tmB, tmC, tmC2, p, stream);
 }
 
 }  // namespace
@@ -540,6 +344,11 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   p.alpha = a.alpha; p.act = a.act; p.epilogue = a.epilogue; p.c_dtype = a.c_dtype; p.r_dtype = a.r_dtype;
   p.atomic = atomic ? 1 : 0;
   p.act_cols = a.act_cols;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("D2R_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   D2R_CHECK_ARG(a.act_cols % 8 == 0, "gemm: act_cols must be a multiple of 8");
   if (atomic) {
     p.variant = EV_ATOMIC;
@@ -569,10 +378,31 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   else               rc = encode_operand(&tmB, a.b, a.n, a.k, b_bi, b_bo, a.ldb, a.b_si, a.b_so, BK);
   if (rc) return rc;
 
+  // C / c2 through TMA bulk stores when their layout obeys the 16-byte rules (always true for the stack's tensors)
+  CUtensorMap tmC, tmC2;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmC2, 0, sizeof(tmC2));
+  {
+    const int es = a.c_dtype == D2R_BF16 ? 2 : 4;
+    const long long q = 16 / es;
+    const bool ok = !atomic && (reinterpret_cast<uintptr_t>(a.c) & 15) == 0 && a.ldc % q == 0 &&
+                    (bi == 1 || (a.c_si % q == 0 && a.c_si != 0)) && (bo == 1 || (a.c_so % q == 0 && a.c_so != 0)) &&
+                    (a.epilogue != D2R_EPI_SQDIFF || (reinterpret_cast<uintptr_t>(a.c2) & 15) == 0);
+    p.tma_store = ok ? 1 : 0;
+    if (ok) {
+      rc = encode_map(&tmC, a.c, es, a.n, a.m, bi, bo, a.ldc, a.c_si, a.c_so, 64 / es, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      if (a.epilogue == D2R_EPI_SQDIFF) {
+        rc = encode_map(&tmC2, a.c2, es, a.n, a.m, bi, bo, a.ldc, a.c_si, a.c_so, 64 / es, 32,
+                        CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+    }
+  }
   const bool amn = a.a_mn_major != 0, bmn = a.b_mn_major != 0;
-  if (bn == 64) return launch_tc_major<64>(amn, bmn, tmA, tmB, p, stream);
-  if (bn == 128) return launch_tc_major<128>(amn, bmn, tmA, tmB, p, stream);
-  return launch_tc_major<256>(amn, bmn, tmA, tmB, p, stream);
+  if (bn == 64) return launch_tc_major<64>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
+  if (bn == 128) return launch_tc_major<128>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
+  return launch_tc_major<256>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
 }
 
 }  // namespace d2r

@@ -1,0 +1,305 @@
+// Epilogue of the tcgen05 GEMM (included by gemm_tc.cu inside namespace d2r::<anon>).
+//
+// 8 epilogue warps.  Warp pair (q, half) shares TMEM lane quarter q (rows q*32 .. q*32+31 of the tile);
+// half 0 takes the first half of the tile's 32-column chunks, half 1 the second, so two warps per
+// scheduler hide each other's TMEM / shared-memory latency.
+//
+// Output path: accumulator chunk (tcgen05.ld, one row per thread) -> bias/act/residual in registers ->
+// 64-byte-swizzled staging tile in shared memory -> ONE TMA bulk tensor store per chunk
+// (cp.async.bulk.tensor ... global.shared::cta).  Measured on B200: the scattered per-thread 16-byte
+// global stores of a direct epilogue cost ~30% of a K=768 GEMM; the bulk store removes them from the LSU.
+// TMA clips rows >= m and columns >= n, so ragged edge tiles take the same path.  C pointers / strides
+// that violate TMA's 16-byte rules, and atomic accumulation (split-K), use direct stores.
+#pragma once
+
+struct NoRes {};
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T>
+__device__ __forceinline__ void st_group(T* ptr, const float (&v)[8], int nvalid) {
+  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+    store8(ptr, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nvalid) Elem<T>::st(ptr + i, v[i]);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void ld_group(const T* ptr, float (&v)[8], int nvalid) {
+  if (nvalid == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+    load8(ptr, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (i < nvalid) ? Elem<T>::ld(ptr + i) : 0.f;
+  }
+}
+
+// Register image of one row's 32 residual values, fetched ahead of the TMEM wait (fast path only).
+template <typename RT> struct ResRegs {};
+template <> struct ResRegs<__nv_bfloat16> { uint4 v[4]; };
+template <> struct ResRegs<float> { float4 v[8]; };
+
+template <typename RT>
+__device__ __forceinline__ void prefetch_res(ResRegs<RT>& pre, const RT* rrow, int col0) {
+  if constexpr (!std::is_same<RT, NoRes>::value) {
+    constexpr int NV = 32 / (16 / sizeof(RT));
+    using Vec = typename std::remove_reference<decltype(pre.v[0])>::type;
+    const Vec* ptr = reinterpret_cast<const Vec*>(rrow + col0);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pre.v[i] = ptr[i];
+  }
+}
+
+template <typename RT>
+__device__ __forceinline__ void unpack_group(const ResRegs<RT>& pre, int g, float (&res)[8]) {
+  if constexpr (std::is_same<RT, __nv_bfloat16>::value) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pre.v[g]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      res[2 * i] = f.x;
+      res[2 * i + 1] = f.y;
+    }
+  } else if constexpr (std::is_same<RT, float>::value) {
+    const float4 a = pre.v[2 * g], b = pre.v[2 * g + 1];
+    res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
+    res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+  }
+}
+
+// ---- staging tile: 32 rows x 64 bytes, CU_TENSOR_MAP_SWIZZLE_64B (16-byte unit u of row r lives at
+//      r*64 + ((u ^ ((r >> 1) & 3)) << 4)); conflict-free for one-row-per-lane writes.
+__device__ __forceinline__ void stage_unit(uint8_t* stage, int lane, int unit, uint4 val) {
+  *reinterpret_cast<uint4*>(stage + lane * 64 + ((unit ^ ((lane >> 1) & 3)) << 4)) = val;
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return u;
+}
+
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Write 32 fp32 values of this lane's row (columns col0 .. col0+31) through the staging tile.
+// bf16: one 64-byte row -> one store; fp32: two rounds of 16 columns.
+template <typename CT>
+__device__ __forceinline__ void tma_store_row32(const CUtensorMap* tm, uint8_t* stage, int lane, const float (&v)[32],
+                                                int col0, int row0, int zi, int zo) {
+  constexpr int ROUNDS = sizeof(CT) == 2 ? 1 : 2;
+#pragma unroll
+  for (int rd = 0; rd < ROUNDS; ++rd) {
+    if (lane == 0) bulk_wait_read0();      // the previous store has finished reading the staging tile
+    __syncwarp();
+    if constexpr (sizeof(CT) == 2) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = v[g * 8 + i];
+        stage_unit(stage, lane, g, pack8_bf16(t));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 val;
+        val.x = __float_as_uint(v[rd * 16 + u * 4 + 0]);
+        val.y = __float_as_uint(v[rd * 16 + u * 4 + 1]);
+        val.z = __float_as_uint(v[rd * 16 + u * 4 + 2]);
+        val.w = __float_as_uint(v[rd * 16 + u * 4 + 3]);
+        stage_unit(stage, lane, u, val);
+      }
+    }
+    fence_proxy_async();                   // generic-proxy smem writes -> visible to the async (TMA) proxy
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(tm, stage, col0 + rd * 16, row0, zi, zo);
+      bulk_commit();
+    }
+  }
+}
+
+// One chunk: 32 accumulator columns of this lane's row -> v[32] (and d[32] for the squared difference).
+//   MODE 0: v = act(alpha*acc + bias) + residual     MODE 1: d = residual - (alpha*acc + bias), v = d*d
+//   MODE 2: v = alpha*acc + bias (atomic accumulation, stored by the caller)
+template <typename CT, typename RT, int MODE, bool FAST>
+__device__ __forceinline__ void epilogue_math(const TcParams& p, const uint32_t (&r)[32], const float* sbias,
+                                              const ResRegs<RT>& pre, const RT* rrow, int col0, float (&v)[32],
+                                              float (&d)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = p.alpha * __uint_as_float(r[g * 8 + i]);
+    if (sbias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
+      t[0] += b0.x; t[1] += b0.y; t[2] += b0.z; t[3] += b0.w;
+      t[4] += b1.x; t[5] += b1.y; t[6] += b1.z; t[7] += b1.w;
+    }
+    float res[8];
+    if constexpr (!std::is_same<RT, NoRes>::value) {
+      if constexpr (FAST) {
+        unpack_group(pre, g, res);
+      } else {
+        const int nvalid = max(0, min(8, p.n - col));
+        ld_group(rrow + col, res, nvalid);
+      }
+    }
+    if constexpr (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        d[g * 8 + i] = res[i] - t[i];
+        t[i] = d[g * 8 + i] * d[g * 8 + i];
+      }
+    } else if constexpr (MODE == 0) {
+      if (p.act != D2R_ACT_NONE && (p.act_cols == 0 || col < p.act_cols)) {
+        if (p.act == D2R_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = fmaxf(t[i], 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = sizeof(CT) == 2 ? fast_tanh(t[i]) : tanhf(t[i]);
+        }
+      }
+      if constexpr (!std::is_same<RT, NoRes>::value) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] += res[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[g * 8 + i] = t[i];
+  }
+}
+
+// direct (non-TMA) stores of one chunk
+template <typename CT, int MODE>
+__device__ __forceinline__ void direct_store(const TcParams& p, CT* crow, CT* c2row, int col0, const float (&v)[32],
+                                             const float (&d)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col >= p.n) break;
+    const int nvalid = min(8, p.n - col);
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = v[g * 8 + i];
+    if constexpr (MODE == 2) {
+      float* dst = reinterpret_cast<float*>(crow) + col;
+      if (nvalid == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        // red.global.add.v4.f32: one L2 reduction per 16 bytes instead of one per element
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t[0]), "f"(t[1]), "f"(t[2]),
+                     "f"(t[3])
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(t[4]), "f"(t[5]), "f"(t[6]),
+                     "f"(t[7])
+                     : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < nvalid) atomicAdd(dst + i, t[i]);
+      }
+    } else {
+      if constexpr (MODE == 1) {
+        float u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = d[g * 8 + i];
+        st_group(c2row + col, u, nvalid);
+      }
+      st_group(crow + col, t, nvalid);
+    }
+  }
+}
+
+template <int BN, typename CT, typename RT, int MODE>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
+                                              uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                              float* sbias_warp, uint8_t* stage, int q, int half, int lane) {
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const bool use_tma = p.tma_store != 0;
+  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const TileCoord tc = decode_tile(p, t, BN);
+    // stage this tile's bias slice in shared memory while the accumulator is still being produced
+    if (p.bias) {
+      const float* bias = p.bias + static_cast<long long>(tc.z) * p.bias_sz;
+      for (int i = lane; i < BN; i += 32) sbias_warp[i] = (tc.n0 + i < p.n) ? __ldg(bias + tc.n0 + i) : 0.f;
+    }
+    __syncwarp();
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+    const int row0 = tc.m0 + q * 32;
+    const long long row = row0 + lane;
+    const bool row_ok = row < p.m;
+    const long long c_off = static_cast<long long>(tc.zo) * p.c_so + static_cast<long long>(tc.zi) * p.c_si +
+                            row * p.ldc;
+    CT* crow = reinterpret_cast<CT*>(p.c) + c_off;
+    CT* c2row = MODE == 1 ? reinterpret_cast<CT*>(p.c2) + c_off : nullptr;
+    const RT* rrow = nullptr;
+    if constexpr (!std::is_same<RT, NoRes>::value)
+      rrow = reinterpret_cast<const RT*>(p.residual) + static_cast<long long>(tc.zo) * p.r_so +
+             static_cast<long long>(tc.zi) * p.r_si + row * p.ldr;
+    const int ncols = min(BN, p.n - tc.n0);
+    const int nchunks = (ncols + 31) >> 5;
+    const int cmid = (nchunks + 1) >> 1;
+    const int cb = half == 0 ? 0 : cmid;
+    const int ce = half == 0 ? cmid : nchunks;
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
+    const float* sb = p.bias ? sbias_warp : nullptr;
+    // residual fast path: whole tile inside the matrix and every row pointer 16-byte aligned (warp-uniform)
+    const bool r_ok = (reinterpret_cast<uintptr_t>(rrow) & 15) == 0;
+    const bool fast = (tc.n0 + BN <= p.n) && __all_sync(0xffffffffu, r_ok && row_ok);
+#pragma unroll 1
+    for (int c = cb; c < ce; ++c) {
+      if (p.debug & 2) continue;
+      uint32_t ra[32];
+      ResRegs<RT> pa;
+      float v[32], d[32];
+      const int col0 = tc.n0 + c * 32;
+      tmem_ld32(taddr + c * 32, ra);
+      if (fast) prefetch_res<RT>(pa, rrow, col0);
+      tmem_ld_wait();
+      if (fast) {
+        epilogue_math<CT, RT, MODE, true>(p, ra, sb ? sb + c * 32 : nullptr, pa, rrow, col0, v, d);
+      } else if (row_ok) {
+        epilogue_math<CT, RT, MODE, false>(p, ra, sb ? sb + c * 32 : nullptr, pa, rrow, col0, v, d);
+      }
+      if (p.debug & 1) continue;
+      if (MODE != 2 && use_tma) {
+        if constexpr (MODE == 1) tma_store_row32<CT>(tmC2, stage, lane, d, col0, row0, tc.zi, tc.zo);
+        tma_store_row32<CT>(tmC, stage, lane, v, col0, row0, tc.zi, tc.zo);
+      } else if (row_ok) {
+        direct_store<CT, MODE>(p, crow, c2row, col0, v, d);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (lane == 0) bulk_wait_all();          // all bulk stores of this warp are complete before the CTA exits
+  __syncwarp();
+}
+
+enum EpiVariant {
+  EV_F32 = 0, EV_F32_RF32, EV_F32_RBF16, EV_BF16, EV_BF16_RF32, EV_BF16_RBF16, EV_SQ_F32, EV_SQ_BF16, EV_ATOMIC
+};
