@@ -150,8 +150,9 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.proc = subprocess.Popen(["stdbuf", "-oL", "nvidia-smi", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True, bufsize=1)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -277,8 +278,10 @@ def own_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = K.L.launch_count()
         e0.record()
+        torch.cuda.nvtx.range_push("timed_hbm" if not from_host else "timed_e2e")   # for `ncu --nvtx-include`
         for _ in range(steps):
             step(from_host)
+        torch.cuda.nvtx.range_pop()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -289,12 +292,18 @@ def own_arm(args):
             ms = float(t.item())
         return ms, launches
 
-    for _ in range(max(args.warmup, 3)):
-        step(False)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # samples cover warm-up + the timed region (both under full load)
+    for _ in range(max(args.warmup, 3)):
+        step(False)
     ms, launches = timed(False, args.steps)
+    if ms < 1500.0:
+        # keep the GPUs under the same load a little longer so that nvidia-smi (100 ms period) sees it; `ms` is the
+        # max over ranks, so every rank runs the same number of extra steps (they contain a collective)
+        for _ in range(int(1500.0 / max(ms / args.steps, 1e-3)) + 1):
+            step(False)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step(True)
