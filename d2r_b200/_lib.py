@@ -54,7 +54,7 @@ class AggArgs(C.Structure):
 class AggBwdArgs(C.Structure):
     _fields_ = [
         ("fwd", AggArgs), ("d_out", Ptr8), ("d_pooled", C.c_void_p),
-        ("d_full", Ptr8), ("d_bvec", Ptr8), ("d_inputs", Ptr8), ("dP", C.c_void_p),
+        ("d_full", Ptr8), ("d_bvec", Ptr8), ("dP", C.c_void_p),
     ]
 
 
@@ -94,6 +94,7 @@ SYMBOLS = {
     "d2r_router_head_bwd": (C.c_int, [_vp, _vp, _vp, Ptr8, _i32, _i32, _i64, _i32, _i32, _vp, _vp, Ptr8, Ptr8, _vp]),
     "d2r_aggregate_fwd": (C.c_int, [C.POINTER(AggArgs), _vp]),
     "d2r_aggregate_bwd": (C.c_int, [C.POINTER(AggBwdArgs), _vp]),
+    "d2r_gate_skip_bwd": (C.c_int, [_vp, _vp, _vp, Ptr8, _i32, _i64, _i64, _i64, _i32, _i32, _vp]),
     "d2r_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "d2r_bias_act_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _i64, _vp]),
     "d2r_l2norm_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i32, _vp]),

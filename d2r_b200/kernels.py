@@ -262,25 +262,31 @@ def aggregate_fwd(full: Sequence[Optional[Tensor]], bvec: Sequence[Optional[Tens
 
 
 def aggregate_bwd(full, bvec, P: Tensor, gate: Tensor, final_layer: bool, d_outs: Sequence[Tensor],
-                  d_pooled: Optional[Tensor], inputs=None, want_d_inputs: bool = False):
-    """-> d_full (list, None for broadcast cells), d_bvec (fp32 [B,D] list), d_inputs (final), dP."""
+                  d_pooled: Optional[Tensor], inputs=None):
+    """-> d_full (list, None for broadcast cells), d_bvec (fp32 [B,D] list), dP."""
     K_ = len(full)
     x0 = full[0]
     B, Ln, D = x0.shape
     n_out = 1 if final_layer else K_
     d_full = [torch.empty_like(x0) if f is not None else None for f in full]
     d_bvec = [torch.empty(B, D, device=x0.device, dtype=torch.float32) if v is not None else None for v in bvec]
-    d_inputs = [torch.empty_like(x0) if (want_d_inputs and final_layer and j > 0) else None for j in range(K_)]
     dP = torch.empty(B, n_out, K_, device=x0.device, dtype=torch.float32)
     b = L.AggBwdArgs()
     b.fwd = _agg_args(full, bvec, inputs or [None] * K_, [None] * 8, P, gate, None, K_, n_out, final_layer, B, Ln, D,
                       L.dt(x0))
     b.d_out = L.ptr8(d_outs)
     b.d_pooled = L.ptr(d_pooled)
-    b.d_full, b.d_bvec, b.d_inputs = L.ptr8(d_full), L.ptr8(d_bvec), L.ptr8(d_inputs)
+    b.d_full, b.d_bvec = L.ptr8(d_full), L.ptr8(d_bvec)
     b.dP = dP.data_ptr()
     L.check(L.lib.d2r_aggregate_bwd(C.byref(b), L.stream()), "aggregate_bwd")
-    return d_full, d_bvec, d_inputs, dP
+    return d_full, d_bvec, dP
+
+
+def gate_skip_bwd(d_out: Tensor, P: Tensor, gate: Tensor, dxs: Sequence[Optional[Tensor]], accumulate_mask: int) -> None:
+    """Final layer: dxs[j][b] (+)= gate[b,j] / S[b] * d_out[b] for j >= 1 (in place; None entries skipped)."""
+    B, Ln, D = d_out.shape
+    L.check(L.lib.d2r_gate_skip_bwd(d_out.data_ptr(), P.data_ptr(), gate.data_ptr(), L.ptr8(dxs), len(dxs), B, Ln, D,
+                                    L.dt(d_out), accumulate_mask, L.stream()), "gate_skip_bwd")
 
 
 def _saf_args(sg, sl, w, bias, bn_w, bn_b, rm, rv, nbt, training, saved) -> L.SafArgs:

@@ -542,9 +542,8 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     xs, z, kv, Kc, final = st["xs"], st["z"], st["kv"], st["Kc"], st["final"]
     cells = CELLS6[:Kc]
     B, Lq, D = xs[0].shape
-    d_full, d_bvec, d_inputs, dP = K.aggregate_bwd(st["full"], st["bvec"], st["norm"], st["gate"], final, d_outs,
-                                                   d_pooled_next, inputs=list(xs) if final else None,
-                                                   want_d_inputs=final)
+    d_full, d_bvec, dP = K.aggregate_bwd(st["full"], st["bvec"], st["norm"], st["gate"], final, d_outs,
+                                         d_pooled_next, inputs=list(xs) if final else None)
     d_norm = dP if d_norm_extra is None else K.axpby(dP, d_norm_extra.contiguous(), 1.0, 1.0)
     d_pooled = _routers_bwd(env, [f"{pre}.{cn}.router" for cn in cells], st["router"], d_norm, final)
 
@@ -563,14 +562,19 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
         d_xs = [acc]
     else:
         d_xs[0] = d_full[0]
-        d_xs[1] = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], d_inputs[1], dz_rows)
-        d_xs[2] = _imrc_bwd(env, pre + ".imrc.sa", xs[2], st["imrc"], d_full[2], d_inputs[2])
-        d_xs[3] = _cmrc_bwd(env, pre + ".cmrc.refine", xs[3], kv, 1, st["cmrc"], d_full[3], d_inputs[3])
+        d_xs[1] = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], None, dz_rows)
+        d_xs[2] = _imrc_bwd(env, pre + ".imrc.sa", xs[2], st["imrc"], d_full[2], None)
+        d_xs[3] = _cmrc_bwd(env, pre + ".cmrc.refine", xs[3], kv, 1, st["cmrc"], d_full[3], None)
+        acc_mask = 0b1110
         if Kc > 4:
-            d_xs[4] = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], d_inputs[4])
-            d5 = d_inputs[5] if d_inputs[5] is not None else torch.zeros_like(xs[5])
-            _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d5, dz_rows)
-            d_xs[5] = d5
+            d_xs[4] = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], None)
+            d_xs[5] = torch.empty_like(xs[5]) if final else torch.zeros_like(xs[5])
+            acc_mask = 0b011110                      # cell 5 (GESC) has no full-size gradient yet: overwrite
+        if final:
+            # gated skip of the final layer (DynamicInteraction.py:108-111): touches only gated samples
+            K.gate_skip_bwd(d_outs[0], st["norm"], st["gate"], d_xs, acc_mask)
+        if Kc > 4:
+            _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d_xs[5], dz_rows)
     dz = kv.backward(env, dz_rows)
     return d_xs, d_pooled, dz
 

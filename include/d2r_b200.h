@@ -140,15 +140,22 @@ typedef struct d2r_agg_args {
 } d2r_agg_args;
 int d2r_aggregate_fwd(const d2r_agg_args* a, void* stream);
 /* backward: d_out[i] (+ optional d_pooled [n_out,B,D]) -> d_full[j] (cell 0: gradient w.r.t. the
- * raw RIC input), d_bvec[j] [B,D], d_inputs[j] (final), dP [B,n_out,K]. */
+ * raw RIC input), d_bvec[j] [B,D], dP [B,n_out,K].  The gated-skip gradient of the final layer's
+ * inputs j >= 1 is produced by d2r_gate_skip_bwd. */
 typedef struct d2r_agg_bwd_args {
   d2r_agg_args fwd;     /* same tensors as forward (out[] unused) */
   d2r_ptr8 d_out;       /* n_out gradients [B,L,D] (dtype fwd.dtype) */
   const float* d_pooled;
-  d2r_ptr8 d_full, d_bvec, d_inputs; /* written; d_bvec fp32 [B,D] */
+  d2r_ptr8 d_full, d_bvec; /* written; d_bvec fp32 [B,D] */
   float* dP;             /* [B,n_out,K], overwritten */
 } d2r_agg_bwd_args;
 int d2r_aggregate_bwd(const d2r_agg_bwd_args* a, void* stream);
+/* Final layer (DynamicInteraction.py:108-111): dx[j][b] (+)= gate[b,j] / S[b] * d_out[b] for j = 1..K-1,
+ * S = sum_j (gate + P).  Bit j of accumulate_mask set: add into an existing gradient and touch only the
+ * samples whose gate is set (p_j < 1e-4/K: essentially never); bit clear: overwrite (zero-fills the
+ * un-gated samples).  NULL dx[j] entries are skipped. */
+int d2r_gate_skip_bwd(const void* d_out, const float* P, const float* gate, d2r_ptr8 dx, int32_t K, int64_t B,
+                      int64_t L, int64_t D, int32_t dtype, int32_t accumulate_mask, void* stream);
 
 /* ---- small fused cell ops (elementwise / row reductions) -------------------------------
  * All take element counts and dtypes explicitly; `rows x cols` row-major with row stride =

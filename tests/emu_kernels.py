@@ -207,7 +207,7 @@ def aggregate_fwd(full, bvec, P, gate, final_layer, inputs=None, want_pooled=Tru
 
 
 @torch.enable_grad()
-def aggregate_bwd(full, bvec, P, gate, final_layer, d_outs, d_pooled, inputs=None, want_d_inputs=False):
+def aggregate_bwd(full, bvec, P, gate, final_layer, d_outs, d_pooled, inputs=None):
     B, Ln, D = full[0].shape
     Kc = len(full)
     dt = full[0].dtype
@@ -231,10 +231,20 @@ def aggregate_bwd(full, bvec, P, gate, final_layer, d_outs, d_pooled, inputs=Non
     loss.backward()
     d_full = [leaves[j].grad.to(dt) if full[j] is not None else None for j in range(Kc)]
     d_bvec = [leaves[j].grad if full[j] is None else None for j in range(Kc)]
-    d_inputs = [None] * Kc
-    if final_layer and want_d_inputs:
-        d_inputs = [None] + [(t.grad if t.grad is not None else torch.zeros_like(t)).to(dt) for t in ins[1:]]
-    return d_full, d_bvec, d_inputs, Pd.grad
+    return d_full, d_bvec, Pd.grad
+
+
+def gate_skip_bwd(d_out, P, gate, dxs, accumulate_mask):
+    B = d_out.shape[0]
+    S = (P[:, 0].sum(-1) + gate.sum(-1)).view(B, 1, 1)
+    for j, dx in enumerate(dxs):
+        if j == 0 or dx is None:
+            continue
+        v = (gate[:, j].view(B, 1, 1) / S * d_out.float()).to(dx.dtype)
+        if (accumulate_mask >> j) & 1:
+            dx.add_(v)
+        else:
+            dx.copy_(v)
 
 
 def _saf_ref(sg, sl, w, bias, bn_w, bn_b, rm, rv, training):

@@ -188,8 +188,15 @@ def test_aggregate(dtype, final, Kc):
         d_pooled = torch.randn(n_out, B, D, device="cuda")
         loss = loss + sum((r.mean(1) * d_pooled[i].double()).sum() for i, r in enumerate(ref))
     loss.backward()
-    d_full, d_bvec, d_inputs, dP = K.aggregate_bwd(full, bvec, P, gate, final, d_outs, d_pooled,
-                                                   inputs if final else None, want_d_inputs=final)
+    d_full, d_bvec, dP = K.aggregate_bwd(full, bvec, P, gate, final, d_outs, d_pooled, inputs if final else None)
+    d_inputs = [None] * Kc
+    if final:
+        d_inputs = [None] + [torch.randn(B, Ln, D, device="cuda").to(dtype) for _ in range(1, Kc)]
+        d_inputs[Kc - 1] = torch.full((B, Ln, D), float("nan"), device="cuda").to(dtype)   # overwritten (mask bit clear)
+        before = [None if t is None else t.clone() for t in d_inputs]
+        K.gate_skip_bwd(d_outs[0], P, gate, d_inputs, ((1 << Kc) - 1) & ~1 & ~(1 << (Kc - 1)))
+        for j in range(1, Kc - 1):
+            d_inputs[j] = d_inputs[j].float() - before[j].float()
     t2 = 3 * tol(dtype)
     assert close(d_full[0], x0d.grad, t2)
     for j in range(1, Kc):
