@@ -278,10 +278,16 @@ def own_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = K.L.launch_count()
         e0.record()
-        torch.cuda.nvtx.range_push("timed_hbm" if not from_host else "timed_e2e")   # for `ncu --nvtx-include`
+        # `ncu --profile-from-start off` captures exactly the HBM-resident timed region (all threads: the
+        # backward kernels are launched from autograd's worker thread, so an NVTX range would miss them)
+        prof = bool(os.environ.get("D2R_PROFILE_RANGE")) and not from_host
+        if prof:
+            torch.cuda.cudart().cudaProfilerStart()
         for _ in range(steps):
             step(from_host)
-        torch.cuda.nvtx.range_pop()
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -394,13 +400,12 @@ def kernel_roofline(fwd_bwd, K, torch):
         byts = (nfull + n_out) * x0.numel() * x0.element_size()
         return timed_call("agg", byts, orig_af, full, bvec, P, gate, final, inputs, want_pooled)
 
-    def agg_b(full, bvec, P, gate, final, d_outs, d_pooled, inputs=None, want_d_inputs=False):
+    def agg_b(full, bvec, P, gate, final, d_outs, d_pooled, inputs=None):
         x0 = full[0]
         nfull = sum(f is not None for f in full)
         n_out = 1 if final else len(full)
-        extra = (len(full) - 1) if (final and want_d_inputs) else 0
-        byts = (n_out + 2 * nfull + extra) * x0.numel() * x0.element_size()
-        return timed_call("agg", byts, orig_ab, full, bvec, P, gate, final, d_outs, d_pooled, inputs, want_d_inputs)
+        byts = (n_out + 2 * nfull) * x0.numel() * x0.element_size()
+        return timed_call("agg", byts, orig_ab, full, bvec, P, gate, final, d_outs, d_pooled, inputs)
 
     K.gemm, K.aggregate_fwd, K.aggregate_bwd = gemm, agg_f, agg_b
     try:

@@ -48,9 +48,36 @@ __global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ z, f
 }
 
 // ------------------------------------------------------------------ act backward + bias gradient
-// block = 8 warps; a block owns 256 columns x ROWS_PER_BLOCK rows; lane owns 8 consecutive columns.
-constexpr int kRowsPerBlock = 128;
-template <typename T>
+// block = 8 warps; a block owns 256 columns x 64 rows; lane owns 8 consecutive columns; every warp keeps
+// 8 independent 16/32-byte row loads in flight (raw vectors, unpacked one row at a time).
+constexpr int kRowsPerBlock = 64;
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void ld(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <typename T, bool ACT>
 __global__ void __launch_bounds__(kThreads) bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y,
                                                                 int act, T* __restrict__ dz, float* __restrict__ db,
                                                                 long long rows, int cols, long long ld) {
@@ -63,29 +90,33 @@ __global__ void __launch_bounds__(kThreads) bias_act_bwd_kernel(const T* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (col < cols) {
-    // 4 independent rows per iteration keep 4-8 16-byte loads in flight per thread
-    for (long long rb = r0 + warp * 4; rb < r1; rb += 32) {
-      float g[4][8], yv[4][8];
+    constexpr int U = ACT ? 4 : 8;
+    for (long long rb = r0 + warp * U; rb < r1; rb += 8 * U) {
+      Raw8<T> g[U], yv[ACT ? U : 1];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long r = rb + u;
         if (r < r1) {
-          load8(dy + r * ld + col, g[u]);
-          if (act != D2R_ACT_NONE) load8(y + r * ld + col, yv[u]);
+          g[u].ld(dy + r * ld + col);
+          if constexpr (ACT) yv[u].ld(y + r * ld + col);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long r = rb + u;
         if (r < r1) {
-          if (act != D2R_ACT_NONE) {
+          float gv[8];
+          g[u].get(gv);
+          if constexpr (ACT) {
+            float yf[8];
+            yv[u].get(yf);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              g[u][j] = act == D2R_ACT_RELU ? (yv[u][j] > 0.f ? g[u][j] : 0.f) : g[u][j] * (1.f - yv[u][j] * yv[u][j]);
-            if (dz) store8(dz + r * ld + col, g[u]);
+              gv[j] = act == D2R_ACT_RELU ? (yf[j] > 0.f ? gv[j] : 0.f) : gv[j] * (1.f - yf[j] * yf[j]);
+            if (dz) store8(dz + r * ld + col, gv);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += g[u][j];
+          for (int j = 0; j < 8; ++j) acc[j] += gv[j];
         }
       }
     }
@@ -395,8 +426,13 @@ int d2r_bias_act_bwd(const void* dy, const void* y, int32_t dtype, int32_t act, 
   D2R_CHECK_ARG(act == D2R_ACT_NONE || y != nullptr, "bias_act_bwd: activation needs y");
   if (rows <= 0) return D2R_OK;
   dim3 grid((cols + 255) / 256, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
-  D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)y, act,
-                                                                                (T*)dz, db, rows, cols, ld));
+  if (act == D2R_ACT_NONE) {
+    D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T, false><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)y, act,
+                                                                                         (T*)dz, db, rows, cols, ld));
+  } else {
+    D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T, true><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)y, act,
+                                                                                        (T*)dz, db, rows, cols, ld));
+  }
   count_launch();
   return check_launch("bias_act_bwd_kernel");
 }

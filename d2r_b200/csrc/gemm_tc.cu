@@ -385,7 +385,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   {
     const int es = a.c_dtype == D2R_BF16 ? 2 : 4;
     const long long q = 16 / es;
-    const bool ok = !atomic && (reinterpret_cast<uintptr_t>(a.c) & 15) == 0 && a.ldc % q == 0 &&
+    const bool ok = (reinterpret_cast<uintptr_t>(a.c) & 15) == 0 && a.ldc % q == 0 &&
                     (bi == 1 || (a.c_si % q == 0 && a.c_si != 0)) && (bo == 1 || (a.c_so % q == 0 && a.c_so != 0)) &&
                     (a.epilogue != D2R_EPI_SQDIFF || (reinterpret_cast<uintptr_t>(a.c2) & 15) == 0);
     p.tma_store = ok ? 1 : 0;

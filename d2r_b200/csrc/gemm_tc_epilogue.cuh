@@ -94,13 +94,22 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// Same, but the tile is ADDED to global memory by the TMA unit (fp32): split-K / gradient accumulation
+// without a single per-thread atomic instruction.
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Write 32 fp32 values of this lane's row (columns col0 .. col0+31) through the staging tile.
 // bf16: one 64-byte row -> one store; fp32: two rounds of 16 columns.
-template <typename CT>
+template <typename CT, bool REDUCE = false>
 __device__ __forceinline__ void tma_store_row32(const CUtensorMap* tm, uint8_t* stage, int lane, const float (&v)[32],
                                                 int col0, int row0, int zi, int zo) {
   constexpr int ROUNDS = sizeof(CT) == 2 ? 1 : 2;
@@ -130,7 +139,8 @@ __device__ __forceinline__ void tma_store_row32(const CUtensorMap* tm, uint8_t* 
     fence_proxy_async();                   // generic-proxy smem writes -> visible to the async (TMA) proxy
     __syncwarp();
     if (lane == 0) {
-      tma_store_4d(tm, stage, col0 + rd * 16, row0, zi, zo);
+      if constexpr (REDUCE) tma_reduce_add_4d(tm, stage, col0 + rd * 16, row0, zi, zo);
+      else tma_store_4d(tm, stage, col0 + rd * 16, row0, zi, zo);
       bulk_commit();
     }
   }
@@ -283,9 +293,13 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         epilogue_math<CT, RT, MODE, false>(p, ra, sb ? sb + c * 32 : nullptr, pa, rrow, col0, v, d);
       }
       if (p.debug & 1) continue;
-      if (MODE != 2 && use_tma) {
+      if (use_tma) {
         if constexpr (MODE == 1) tma_store_row32<CT>(tmC2, stage, lane, d, col0, row0, tc.zi, tc.zo);
-        tma_store_row32<CT>(tmC, stage, lane, v, col0, row0, tc.zi, tc.zo);
+        if constexpr (MODE == 2) {
+          if constexpr (sizeof(CT) == 4) tma_store_row32<CT, true>(tmC, stage, lane, v, col0, row0, tc.zi, tc.zo);
+        } else {
+          tma_store_row32<CT>(tmC, stage, lane, v, col0, row0, tc.zi, tc.zo);
+        }
       } else if (row_ok) {
         direct_store<CT, MODE>(p, crow, c2row, col0, v, d);
       }
