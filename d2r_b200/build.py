@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libd2r_b200.so")
 SOURCES = ["c_api.cu", "gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "router.cu", "aggregate.cu", "saf.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", "gemm_tc_epilogue.cuh", os.path.join("..", "..", "include", "d2r_b200.h")]
+HEADERS = ["common.cuh", "ptx.cuh", "gemm_tc_epilogue.cuh", "gemm_tc2.cuh", os.path.join("..", "..", "include", "d2r_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

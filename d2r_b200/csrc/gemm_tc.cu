@@ -44,6 +44,7 @@ struct TcCfg {
 
 struct TcParams {
   int m, n, k;
+  int bm;            // rows per tile: 128 (one CTA) or 256 (CTA pair, cta_group::2)
   int batch_inner;
   int m_tiles, n_tiles, k_blocks, split_k, kb_per_split;
   long long num_tiles;
@@ -71,7 +72,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long t,
   t /= p.split_k;
   int mb = static_cast<int>(t % p.m_tiles);
   int z = static_cast<int>(t / p.m_tiles);
-  tc.m0 = mb * BM;
+  tc.m0 = mb * p.bm;
   tc.n0 = nb * bn;
   tc.z = z;
   tc.zi = z % p.batch_inner;
@@ -212,17 +213,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* sb = sbias + (warp - 2) * BN;
     const int half = (warp - 2) >> 2;
     uint8_t* stg = store_stage + (warp - 2) * 2048;
+    const TileWalk walk{static_cast<long long>(blockIdx.x), static_cast<long long>(gridDim.x), 0, -1};
     using bf16 = __nv_bfloat16;
     switch (p.variant) {
-      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
-      default:            epilogue_loop<BN, float, NoRes, 2>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane); break;
+      case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_F32_RF32:   epilogue_loop<BN, float, float, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_F32_RBF16:  epilogue_loop<BN, float, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_BF16:       epilogue_loop<BN, bf16, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_BF16_RF32:  epilogue_loop<BN, bf16, float, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      default:            epilogue_loop<BN, float, NoRes, 2>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
     }
   }
 
@@ -233,6 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
+
+#include "gemm_tc2.cuh"
 
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -294,6 +298,30 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   return check_launch("gemm_tc_kernel");
 }
 
+template <bool A_MN, bool B_MN>
+int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+               const TcParams& p, cudaStream_t stream) {
+  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long max_pairs = num_sms() / 2;
+  const long long pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  kern<<<(unsigned)(2 * pairs), kTcThreads, Tc2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+  count_launch();
+  return check_launch("gemm_tc2_kernel");
+}
+
+int launch_tc2_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                     const CUtensorMap& tmC2, const TcParams& p, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_tc2<false, false>(tmA, tmB, tmC, tmC2, p, stream);
+  if (!a_mn && b_mn) return launch_tc2<false, true>(tmA, tmB, tmC, tmC2, p, stream);
+  if (a_mn && !b_mn) return launch_tc2<true, false>(tmA, tmB, tmC, tmC2, p, stream);
+  return launch_tc2<true, true>(tmA, tmB, tmC, tmC2, p, stream);
+}
+
 template <int BN>
 int launch_tc_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                     const CUtensorMap& tmC2, const TcParams& p, cudaStream_t stream) {
@@ -319,13 +347,25 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   int split_k = a.split_k > 1 ? a.split_k : 1;
 
   int bn = a.tile_n;
-  if (bn == 0) bn = a.n <= 64 ? 64 : (a.n <= 128 ? 128 : 256);
+  bool pair = false;                       // CTA-pair kernel: 256 x 256 tiles, tcgen05.mma.cta_group::2
+  if (bn == 512) {
+    pair = true;
+    bn = 256;
+  } else if (bn == 0) {
+    bn = a.n <= 64 ? 64 : (a.n <= 128 ? 128 : 256);
+    if (bn == 256) {
+      const long long work = 1LL * ((a.m + 255) / 256) * ((a.n + 255) / 256) * split_k * a.batch;
+      pair = work >= 32;                  // enough 256x256 tiles to occupy the 74 CTA pairs
+    }
+  }
   D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "gemm: tile_n %d unsupported", bn);
+  const int bm = pair ? 2 * BM : BM;
 
   TcParams p;
   p.m = a.m; p.n = a.n; p.k = a.k;
+  p.bm = bm;
   p.batch_inner = bi;
-  p.m_tiles = (a.m + BM - 1) / BM;
+  p.m_tiles = (a.m + bm - 1) / bm;
   p.n_tiles = (a.n + bn - 1) / bn;
   p.k_blocks = (a.k + BK - 1) / BK;
   if (split_k > p.k_blocks) split_k = p.k_blocks;
@@ -374,7 +414,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   if (!a.a_mn_major) rc = encode_operand(&tmA, a.a, a.k, a.m, a_bi, a_bo, a.lda, a.a_si, a.a_so, BM);
   else               rc = encode_operand(&tmA, a.a, a.m, a.k, a_bi, a_bo, a.lda, a.a_si, a.a_so, BK);
   if (rc) return rc;
-  if (!a.b_mn_major) rc = encode_operand(&tmB, a.b, a.k, a.n, b_bi, b_bo, a.ldb, a.b_si, a.b_so, bn);
+  if (!a.b_mn_major) rc = encode_operand(&tmB, a.b, a.k, a.n, b_bi, b_bo, a.ldb, a.b_si, a.b_so, pair ? 128 : bn);
   else               rc = encode_operand(&tmB, a.b, a.n, a.k, b_bi, b_bo, a.ldb, a.b_si, a.b_so, BK);
   if (rc) return rc;
 
@@ -400,6 +440,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
     }
   }
   const bool amn = a.a_mn_major != 0, bmn = a.b_mn_major != 0;
+  if (pair) return launch_tc2_major(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 64) return launch_tc_major<64>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 128) return launch_tc_major<128>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   return launch_tc_major<256>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);

@@ -239,14 +239,23 @@ __device__ __forceinline__ void direct_store(const TcParams& p, CT* crow, CT* c2
   }
 }
 
+// TileWalk: which tiles this CTA visits (persistent stride) and, for a CTA pair (cta_group::2), which 128-row half
+// of the 256-row pair tile it owns and where the accumulator-free signal goes (the leader CTA's barrier).
+struct TileWalk {
+  long long first, step;
+  int m_off;        // row offset of this CTA inside the tile (0, or 128 for the odd CTA of a pair)
+  int remote_cta;   // < 0: arrive on the local tmem_empty barrier; >= 0: arrive on that CTA's barrier (mapa)
+};
+
 template <int BN, typename CT, typename RT, int MODE>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
-                                              float* sbias_warp, uint8_t* stage, int q, int half, int lane) {
+                                              float* sbias_warp, uint8_t* stage, int q, int half, int lane,
+                                              const TileWalk w) {
   int acc = 0;
   uint32_t acc_phase = 0;
   const bool use_tma = p.tma_store != 0;
-  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+  for (long long t = w.first; t < p.num_tiles; t += w.step) {
     const TileCoord tc = decode_tile(p, t, BN);
     // stage this tile's bias slice in shared memory while the accumulator is still being produced
     if (p.bias) {
@@ -256,7 +265,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     __syncwarp();
     mbar_wait(&tmem_full[acc], acc_phase);
     tc_fence_after();
-    const int row0 = tc.m0 + q * 32;
+    const int row0 = tc.m0 + w.m_off + q * 32;
     const long long row = row0 + lane;
     const bool row_ok = row < p.m;
     const long long c_off = static_cast<long long>(tc.zo) * p.c_so + static_cast<long long>(tc.zi) * p.c_si +
@@ -306,7 +315,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if (lane == 0) {
+      if (w.remote_cta < 0) mbar_arrive(&tmem_empty[acc]);
+      else mbar_arrive_cluster(&tmem_empty[acc], static_cast<uint32_t>(w.remote_cta));
+    }
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }

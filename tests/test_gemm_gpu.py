@@ -46,6 +46,14 @@ def test_tc_majors(a_mn, b_mn, tile_n):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("m,n,k", [(512, 512, 192), (300, 333, 72), (1000, 768, 768)])
+def test_tc_cta_pair(a_mn, b_mn, m, n, k):
+    """tile_n=512 forces the cta_group::2 kernel (256x256 tiles on a CTA pair), incl. ragged edges."""
+    err, scale = _run(torch.bfloat16, m, n, k, a_mn, b_mn, 512, batch=2)
+    assert err <= 2e-3 * scale + 1e-3, (err, scale)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", MAJORS)
 @pytest.mark.parametrize("m,n,k", [(200, 50, 72), (128, 48, 128), (130, 197, 768), (77, 300, 40)])
 def test_tc_ragged(a_mn, b_mn, m, n, k):
     err, scale = _run(torch.bfloat16, m, n, k, a_mn, b_mn, batch=3)
