@@ -87,6 +87,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nh = tc.n0 + static_cast<int>(rank) * Cfg::HALF_N;
         const int azi = p.a_bcast_i ? 0 : tc.zi, azo = p.a_bcast_o ? 0 : tc.zo;
         const int bzi = p.b_bcast_i ? 0 : tc.zi, bzo = p.b_bcast_o ? 0 : tc.zo;
+        // (an explicit TMA L2 prefetch of the next tile's A rows was measured and made every shape slower:
+        //  it competes with the demand loads for the same L2 request bandwidth)
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
