@@ -34,8 +34,8 @@ template <int BN>
 struct TcCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;   // power of two; accumulators at 0 and BN
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = 8 * BN * 4;   // one private bias slice per epilogue warp
   static constexpr int STORE_BYTES = 8 * 2048;    // one 32-row x 64-byte staging tile per epilogue warp
@@ -355,10 +355,12 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
     bn = a.n <= 64 ? 64 : (a.n <= 128 ? 128 : 256);
     if (bn == 256) {
       const long long work = 1LL * ((a.m + 255) / 256) * ((a.n + 255) / 256) * split_k * a.batch;
-      pair = work >= 32;                  // enough 256x256 tiles to occupy the 74 CTA pairs
+      // enough 256x256 tiles to occupy the 74 CTA pairs, and a shape where halving the B fill pays (measured:
+      // long k, wide n or very tall m; the 12800-row K=768 projections are faster on single-CTA tiles)
+      pair = work >= 32 && (a.k >= 1536 || a.n >= 1536 || a.m >= 16384);
     }
   }
-  D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "gemm: tile_n %d unsupported", bn);
+  D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 192 || bn == 256, "gemm: tile_n %d unsupported", bn);
   const int bm = pair ? 2 * BM : BM;
 
   TcParams p;
@@ -443,6 +445,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   if (pair) return launch_tc2_major(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 64) return launch_tc_major<64>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 128) return launch_tc_major<128>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
+  if (bn == 192) return launch_tc_major<192>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   return launch_tc_major<256>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
 }
 

@@ -16,6 +16,46 @@ from . import _lib as L
 Tensor = torch.Tensor
 
 
+class _ZeroArena:
+    """Small fp32 gradients that kernels accumulate into atomically (bias gradients, router head gradients...)
+    are carved out of ONE pre-zeroed buffer per backward pass instead of ~250 separate torch.zeros launches.
+    A fresh buffer is taken for every pass (never re-zeroed in place), so gradients of an earlier step that
+    still alias an old arena stay valid."""
+
+    CHUNK = 1 << 20
+
+    def __init__(self):
+        self.buf: Optional[Tensor] = None
+        self.off = 0
+
+    def reset(self) -> None:
+        self.buf, self.off = None, 0
+
+    def take(self, n: int, device: torch.device) -> Tensor:
+        n_al = (n + 63) // 64 * 64
+        if n_al > self.CHUNK // 4:
+            return torch.zeros(n, device=device, dtype=torch.float32)
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            self.buf, self.off = torch.zeros(self.CHUNK, device=device, dtype=torch.float32), 0
+        v = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return v
+
+
+_zero_arena = _ZeroArena()
+
+
+def zeros_f32(shape, device: torch.device) -> Tensor:
+    n = 1
+    for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+        n *= int(d)
+    return _zero_arena.take(n, device).view(shape)
+
+
+def zero_arena_reset() -> None:
+    _zero_arena.reset()
+
+
 def gemm(a: Tensor, b: Tensor, c: Tensor, *, m: int, n: int, k: int, lda: int, ldb: int, ldc: int,
          a_mn: bool = False, b_mn: bool = False, batch: int = 1, batch_inner: int = 1,
          a_str: Tuple[int, int] = (0, 0), b_str: Tuple[int, int] = (0, 0), c_str: Tuple[int, int] = (0, 0),
@@ -101,7 +141,7 @@ def bias_act_bwd(dy: Tensor, y: Optional[Tensor], act: int, want_dz: bool, want_
     rows = dy.numel() // cols
     assert dy.is_contiguous()
     dz = torch.empty_like(dy) if (want_dz and act != L.ACT_NONE) else None
-    db = torch.zeros(cols, device=dy.device, dtype=torch.float32) if want_db else None
+    db = zeros_f32(cols, dy.device) if want_db else None
     if dz is not None or db is not None:
         L.check(L.lib.d2r_bias_act_bwd(dy.data_ptr(), L.ptr(y), L.dt(dy), act, L.ptr(dz), L.ptr(db), rows, cols,
                                        cols, L.stream()), "bias_act_bwd")
@@ -228,8 +268,8 @@ def router_head_bwd(d_norm: Tensor, raw: Tensor, hid: Tensor, w2: Sequence[Tenso
     n_out = raw.shape[1]
     d_hid = torch.empty_like(hid)
     d_logit = torch.empty_like(raw)
-    d_w2 = [torch.zeros_like(w) for w in w2]
-    d_b2 = [torch.zeros(n_out, device=hid.device, dtype=torch.float32) for _ in w2]
+    d_w2 = [zeros_f32(w.shape, hid.device) for w in w2]
+    d_b2 = [zeros_f32(n_out, hid.device) for _ in w2]
     L.check(L.lib.d2r_router_head_bwd(d_norm.data_ptr(), raw.data_ptr(), hid.data_ptr(), L.ptr8(w2), K_, n_out, B, H,
                                       int(final_layer), d_hid.data_ptr(), d_logit.data_ptr(), L.ptr8(d_w2),
                                       L.ptr8(d_b2), L.stream()), "router_head_bwd")
@@ -319,8 +359,8 @@ def saf_bwd(d_out: Tensor, sg, sl, w, bias, bn_w, bn_b, rm, rv, training: bool, 
     B, Ln, D = sl.shape
     dev = sl.device
     d_sg, d_sl = torch.empty_like(sg), torch.empty_like(sl)
-    d_w = torch.zeros(D, device=dev)
-    d_bias, d_bn_w, d_bn_b = torch.zeros(1, device=dev), torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    d_w = zeros_f32(D, dev)
+    d_bias, d_bn_w, d_bn_b = zeros_f32(1, dev), zeros_f32(1, dev), zeros_f32(1, dev)
     scratch = torch.empty(B * D + B * (Ln + 1) + 8, device=dev)
     b = L.SafBwdArgs()
     b.fwd = _saf_args(sg, sl, w, bias, bn_w, bn_b, rm, rv, None, training, saved)

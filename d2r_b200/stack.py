@@ -99,18 +99,6 @@ class Env:
 
 
 # ----------------------------------------------------------------------------- linear helpers
-_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
-
-
-def _side_stream(device: torch.device) -> "torch.cuda.Stream":
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    st = _SIDE_STREAMS.get(idx)
-    if st is None:
-        st = torch.cuda.Stream(device=idx)
-        _SIDE_STREAMS[idx] = st
-    return st
-
-
 def _split_k(m_out: int, n_out: int, k: int, tc: bool) -> int:
     if tc:
         tiles = ((m_out + 127) // 128) * ((n_out + 255) // 256)
@@ -135,19 +123,8 @@ def lin_bwd(env: Env, dy: Tensor, x: Tensor, ldx: int, W: Tensor, names: Sequenc
     dz, db = K.bias_act_bwd(dy, y, act, True, True)
     tc = W.dtype == torch.bfloat16
     dW = torch.empty(N, Kd, device=W.device, dtype=torch.float32)
-    # The weight gradient and the data gradient only share their input dz: run the weight gradient on a side
-    # stream so that the CTAs of one persistent GEMM fill the SMs the other leaves idle in its last, partial
-    # wave (768 tiles on 148 SMs = 5.19 waves) and the two prologues overlap.  Joined before returning.
-    fork = need_dx and dz.is_cuda and M >= 4096
-    if fork:
-        main, side = torch.cuda.current_stream(), _side_stream(dz.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            K.gemm(dz, x, dW, m=N, n=Kd, k=M, lda=N, ldb=ldx, ldc=Kd, a_mn=True, b_mn=True,
-                   split_k=_split_k(N, Kd, M, tc))
-    else:
-        K.gemm(dz, x, dW, m=N, n=Kd, k=M, lda=N, ldb=ldx, ldc=Kd, a_mn=True, b_mn=True,
-               split_k=_split_k(N, Kd, M, tc))
+    K.gemm(dz, x, dW, m=N, n=Kd, k=M, lda=N, ldb=ldx, ldc=Kd, a_mn=True, b_mn=True,
+           split_k=_split_k(N, Kd, M, tc))
     r = 0
     for nme in names:
         rows = env.P[nme + ".weight"].shape[0]
@@ -161,8 +138,6 @@ def lin_bwd(env: Env, dy: Tensor, x: Tensor, ldx: int, W: Tensor, names: Sequenc
         dx_ld = Kd
     K.gemm(dz, W, dx_out, m=M, n=Kd, k=N, lda=N, ldb=Kd, ldc=dx_ld, b_mn=True, residual=residual,
            ldr=dx_ld if residual is not None else 0)
-    if fork:
-        main.wait_stream(side)
     return dx_out
 
 
@@ -636,6 +611,7 @@ def stack_backward(env: Env, state, d_out: Optional[Tensor], d_sim: Optional[Ten
     """-> (dx, dz) in env.cd; parameter gradients are left in env.G."""
     states, paths, R, Kc = state["states"], state["paths"], state["R"], state["Kc"]
     x, z = state["x"], state["z"]
+    K.zero_arena_reset()
     B, Lq, D = x.shape
     pres = layer_prefixes(R)
     Pn = paths.shape[1]

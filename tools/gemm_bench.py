@@ -15,6 +15,13 @@ CASES = {
     # name: (m, n, k, a_mn, b_mn, extra kwargs)
     "fwd_nt": (32768, 768, 768, False, False, dict(bias=True, out="bf16")),
     "fwd_nt_bn128": (32768, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=128)),
+    "fwd_nt_bn192": (32768, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=192)),
+    "fwd_nt_bn256": (32768, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=256)),
+    "dgrad_bn192": (32768, 768, 768, False, True, dict(out="bf16", tile_n=192)),
+    "img_nt": (12800, 768, 768, False, False, dict(bias=True, out="bf16")),
+    "img_nt_bn192": (12800, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=192)),
+    "img_nt_bn256": (12800, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=256)),
+    "img_nt_bn128": (12800, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=128)),
     "fwd_nt_res": (32768, 768, 768, False, False, dict(bias=True, out="bf16", residual=True, act=L.ACT_RELU)),
     "dgrad_nn": (32768, 768, 768, False, True, dict(out="bf16")),
     "wgrad_tt": (768, 768, 32768, True, True, dict(out="f32", split_k=16)),
