@@ -196,6 +196,7 @@ def own_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = BATCH_PER_GPU
 
@@ -415,8 +416,11 @@ def kernel_roofline(fwd_bwd, K, torch):
             v.clear()
         nsteps = 2
         for _ in range(nsteps):
+            # park the GPU for ~80 ms so that the host enqueues the whole step ahead of it: the events then
+            # bracket back-to-back kernel execution, not host launch latency
+            torch.cuda._sleep(int(0.08 * 1.9e9))
             fwd_bwd()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
     finally:
         K.gemm, K.aggregate_fwd, K.aggregate_bwd = orig_gemm, orig_af, orig_ab
     gms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["gemm"]) / nsteps
