@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libd2r_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_STD, EPI_SQDIFF = 0, 1
+EPI_STD, EPI_SQDIFF, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2, 3
 ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH}
 
 

@@ -120,6 +120,8 @@ int gemm_simt(const d2r_gemm_args& a, cudaStream_t stream) {
   D2R_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0 && a.batch > 0 && a.batch_inner > 0, "gemm: empty problem");
   D2R_CHECK_ARG(a.batch % a.batch_inner == 0, "gemm: batch %d not a multiple of batch_inner %d", a.batch,
                 a.batch_inner);
+  D2R_CHECK_ARG(a.epilogue == D2R_EPI_STD || a.epilogue == D2R_EPI_SQDIFF,
+                "gemm(fp32): the fused softmax epilogues exist on the bf16 tensor-core path only");
   D2R_CHECK_ARG(a.epilogue == D2R_EPI_STD || (a.residual && a.c2), "gemm: SQDIFF needs residual and c2");
   int split_k = a.split_k > 1 ? a.split_k : 1;
   SimtParams p;

@@ -224,6 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
       case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
       case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_SOFTMAX_BF16:     epilogue_loop<BN, bf16, NoRes, 3>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_SOFTMAX_BWD_BF16: epilogue_loop<BN, bf16, bf16, 4>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
       default:            epilogue_loop<BN, float, NoRes, 2>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
     }
   }
@@ -342,7 +344,15 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   D2R_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0 && a.a_so % 8 == 0 && a.a_si % 8 == 0 && a.b_so % 8 == 0 &&
                     a.b_si % 8 == 0,
                 "gemm(bf16): lda/ldb/batch strides must be multiples of 8 elements (TMA 16-byte rule)");
-  D2R_CHECK_ARG(a.epilogue == D2R_EPI_STD || (a.residual && a.c2), "gemm: SQDIFF needs residual and c2");
+  D2R_CHECK_ARG(a.epilogue != D2R_EPI_SQDIFF || (a.residual && a.c2), "gemm: SQDIFF needs residual and c2");
+  const bool softmax_epi = a.epilogue == D2R_EPI_SOFTMAX || a.epilogue == D2R_EPI_SOFTMAX_BWD;
+  if (softmax_epi) {
+    D2R_CHECK_ARG(a.n <= 256 && a.split_k <= 1 && !a.accumulate && a.act == D2R_ACT_NONE && !a.bias &&
+                      a.c_dtype == D2R_BF16,
+                  "gemm: the fused softmax epilogues need n <= 256 (one N tile), bf16 output, no bias/act/split-K");
+    D2R_CHECK_ARG(a.epilogue != D2R_EPI_SOFTMAX_BWD || (a.residual && a.r_dtype == D2R_BF16),
+                  "gemm: SOFTMAX_BWD needs the bf16 probabilities as residual");
+  }
   const int bo = a.batch / a.batch_inner, bi = a.batch_inner;
   int split_k = a.split_k > 1 ? a.split_k : 1;
 
@@ -357,10 +367,11 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
       const long long work = 1LL * ((a.m + 255) / 256) * ((a.n + 255) / 256) * split_k * a.batch;
       // enough 256x256 tiles to occupy the 74 CTA pairs, and a shape where halving the B fill pays (measured:
       // long k, wide n or very tall m; the 12800-row K=768 projections are faster on single-CTA tiles)
-      pair = work >= 32 && (a.k >= 1536 || a.n >= 1536 || a.m >= 16384);
+      pair = !softmax_epi && work >= 32 && (a.k >= 1536 || a.n >= 1536 || a.m >= 16384);
     }
   }
   D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 192 || bn == 256, "gemm: tile_n %d unsupported", bn);
+  D2R_CHECK_ARG(!softmax_epi || (!pair && bn >= a.n), "gemm: the softmax epilogues need the whole row in one tile");
   const int bm = pair ? 2 * BM : BM;
 
   TcParams p;
@@ -394,6 +405,10 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   D2R_CHECK_ARG(a.act_cols % 8 == 0, "gemm: act_cols must be a multiple of 8");
   if (atomic) {
     p.variant = EV_ATOMIC;
+  } else if (a.epilogue == D2R_EPI_SOFTMAX) {
+    p.variant = EV_SOFTMAX_BF16;
+  } else if (a.epilogue == D2R_EPI_SOFTMAX_BWD) {
+    p.variant = EV_SOFTMAX_BWD_BF16;
   } else if (a.epilogue == D2R_EPI_SQDIFF) {
     D2R_CHECK_ARG(a.r_dtype == a.c_dtype, "gemm: SQDIFF needs residual and outputs of the same dtype");
     p.variant = a.c_dtype == D2R_BF16 ? EV_SQ_BF16 : EV_SQ_F32;

@@ -171,6 +171,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       case EV_BF16_RBF16: epilogue_loop<BN, bf16, bf16, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
       case EV_SQ_F32:     epilogue_loop<BN, float, float, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
       case EV_SQ_BF16:    epilogue_loop<BN, bf16, bf16, 1>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_SOFTMAX_BF16:     epilogue_loop<BN, bf16, NoRes, 3>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
+      case EV_SOFTMAX_BWD_BF16: epilogue_loop<BN, bf16, bf16, 4>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
       default:            epilogue_loop<BN, float, NoRes, 2>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;
     }
   }

@@ -286,6 +286,67 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     // residual fast path: whole tile inside the matrix and every row pointer 16-byte aligned (warp-uniform)
     const bool r_ok = (reinterpret_cast<uintptr_t>(rrow) & 15) == 0;
     const bool fast = (tc.n0 + BN <= p.n) && __all_sync(0xffffffffu, r_ok && row_ok);
+    if constexpr (MODE == 3 || MODE == 4) {
+      // ---- row softmax fused into the score GEMM (MODE 3) / its backward fused into the dP GEMM (MODE 4).
+      // The whole key dimension is one N tile (n <= BN), so a thread's TMEM lane holds its complete row: the
+      // row statistics need no cross-thread traffic at all, and S / dP never touch HBM.  Both warps of a pair
+      // compute the statistics of the full row (cheap TMEM re-reads) and then write their own half.
+      float stat0 = MODE == 3 ? -INFINITY : 0.f, stat1 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {          // pass 1: row max (fwd) / sum dP*P (bwd)
+        uint32_t ra[32];
+        tmem_ld32(taddr + c * 32, ra);
+        tmem_ld_wait();
+        if constexpr (MODE == 3) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < ncols) stat0 = fmaxf(stat0, p.alpha * __uint_as_float(ra[i]));
+        } else if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pr[8];
+            ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stat0 = fmaf(p.alpha * __uint_as_float(ra[g * 8 + i]), pr[i], stat0);
+          }
+        }
+      }
+      if constexpr (MODE == 3) {
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {        // pass 2: sum of exponentials
+          uint32_t ra[32];
+          tmem_ld32(taddr + c * 32, ra);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < ncols) stat1 += __expf(p.alpha * __uint_as_float(ra[i]) - stat0);
+        }
+        stat1 = 1.f / stat1;
+      }
+#pragma unroll 1
+      for (int c = cb; c < ce; ++c) {              // pass 3: this warp's half of the row -> P (or dS)
+        uint32_t ra[32];
+        float v[32], d[32];
+        tmem_ld32(taddr + c * 32, ra);
+        tmem_ld_wait();
+        if constexpr (MODE == 3) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = (c * 32 + i < ncols) ? __expf(p.alpha * __uint_as_float(ra[i]) - stat0) * stat1 : 0.f;
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pr[8];
+            if (row_ok) ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              v[g * 8 + i] = row_ok ? pr[i] * (p.alpha * __uint_as_float(ra[g * 8 + i]) - stat0) : 0.f;
+          }
+        }
+        if (use_tma) tma_store_row32<CT>(tmC, stage, lane, v, c * 32, row0, tc.zi, tc.zo);
+        else if (row_ok) direct_store<CT, 0>(p, crow, c2row, c * 32, v, d);
+      }
+    } else {
 #pragma unroll 1
     for (int c = cb; c < ce; ++c) {
       if (p.debug & 2) continue;
@@ -313,6 +374,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         direct_store<CT, MODE>(p, crow, c2row, col0, v, d);
       }
     }
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -327,5 +389,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
 }
 
 enum EpiVariant {
-  EV_F32 = 0, EV_F32_RF32, EV_F32_RBF16, EV_BF16, EV_BF16_RF32, EV_BF16_RBF16, EV_SQ_F32, EV_SQ_BF16, EV_ATOMIC
+  EV_F32 = 0, EV_F32_RF32, EV_F32_RBF16, EV_BF16, EV_BF16_RF32, EV_BF16_RBF16, EV_SQ_F32, EV_SQ_BF16, EV_ATOMIC,
+  EV_SOFTMAX_BF16, EV_SOFTMAX_BWD_BF16
 };

@@ -192,6 +192,11 @@ def _small_bwd(env: Env, dy32: Tensor, xc: Tensor, name: str, *, y: Optional[Ten
 
 
 # ----------------------------------------------------------------------------- attention core
+def _fused_softmax(cd: torch.dtype, Lc: int) -> bool:
+    """The tensor-core GEMM can finish the softmax in its epilogue when a score row fits one N tile."""
+    return cd == torch.bfloat16 and Lc <= 256
+
+
 def attn_fwd(q: Tensor, q_ld: int, k: Tensor, k_ld: int, v: Tensor, v_ld: int, B: int, Lq: int, Lc: int, D: int,
              heads: int, alpha: float, cd: torch.dtype, *, residual: Optional[Tensor] = None,
              epilogue: int = L.EPI_STD, c2: Optional[Tensor] = None):
@@ -199,11 +204,18 @@ def attn_fwd(q: Tensor, q_ld: int, k: Tensor, k_ld: int, v: Tensor, v_ld: int, B
     dh = D // heads
     Lcp = pad8(Lc)
     dev = q.device
-    S = torch.empty(B, heads, Lq, Lcp, device=dev, dtype=torch.float32)
-    K.gemm(q, k, S, m=Lq, n=Lc, k=dh, lda=q_ld, ldb=k_ld, ldc=Lcp, batch=B * heads, batch_inner=heads,
-           a_str=(Lq * q_ld, dh), b_str=(Lc * k_ld, dh), c_str=(heads * Lq * Lcp, Lq * Lcp), alpha=alpha)
-    P = K.softmax_fwd(S, Lc, 1.0, cd)
-    del S
+    if _fused_softmax(cd, Lc):
+        # scores stay in TMEM: the GEMM's epilogue normalises the row and writes P directly
+        P = torch.empty(B, heads, Lq, Lcp, device=dev, dtype=cd)
+        K.gemm(q, k, P, m=Lq, n=Lc, k=dh, lda=q_ld, ldb=k_ld, ldc=Lcp, batch=B * heads, batch_inner=heads,
+               a_str=(Lq * q_ld, dh), b_str=(Lc * k_ld, dh), c_str=(heads * Lq * Lcp, Lq * Lcp), alpha=alpha,
+               epilogue=L.EPI_SOFTMAX)
+    else:
+        S = torch.empty(B, heads, Lq, Lcp, device=dev, dtype=torch.float32)
+        K.gemm(q, k, S, m=Lq, n=Lc, k=dh, lda=q_ld, ldb=k_ld, ldc=Lcp, batch=B * heads, batch_inner=heads,
+               a_str=(Lq * q_ld, dh), b_str=(Lc * k_ld, dh), c_str=(heads * Lq * Lcp, Lq * Lcp), alpha=alpha)
+        P = K.softmax_fwd(S, Lc, 1.0, cd)
+        del S
     out = torch.empty(B, Lq, D, device=dev, dtype=cd)
     K.gemm(P, v, out, m=Lq, n=dh, k=Lc, lda=Lcp, ldb=v_ld, ldc=D, b_mn=True, batch=B * heads, batch_inner=heads,
            a_str=(heads * Lq * Lcp, Lq * Lcp), b_str=(Lc * v_ld, dh), c_str=(Lq * D, dh),
@@ -219,13 +231,20 @@ def attn_bwd(dO: Tensor, do_ld: int, sign: float, P: Tensor, q: Tensor, q_ld: in
     dh = D // heads
     Lcp = pad8(Lc)
     HS = heads * Lq * Lcp
-    dP = torch.empty(B, heads, Lq, Lcp, device=dO.device, dtype=torch.float32)
-    K.gemm(dO, v, dP, m=Lq, n=Lc, k=dh, lda=do_ld, ldb=v_ld, ldc=Lcp, batch=B * heads, batch_inner=heads,
-           a_str=(Lq * do_ld, dh), b_str=(Lc * v_ld, dh), c_str=(HS, Lq * Lcp), alpha=sign)
     K.gemm(P, dO, dv, m=Lc, n=dh, k=Lq, lda=Lcp, ldb=do_ld, ldc=dv_ld, a_mn=True, b_mn=True, batch=B * heads,
            batch_inner=heads, a_str=(HS, Lq * Lcp), b_str=(Lq * do_ld, dh), c_str=(Lc * dv_ld, dh), alpha=sign)
-    dS = K.softmax_bwd(P, dP, Lc, 1.0, cd)
-    del dP
+    if _fused_softmax(cd, Lc):
+        # dS = P * (dP - sum(dP * P)) straight out of the dP accumulator; dP never reaches HBM
+        dS = torch.empty(B, heads, Lq, Lcp, device=dO.device, dtype=cd)
+        K.gemm(dO, v, dS, m=Lq, n=Lc, k=dh, lda=do_ld, ldb=v_ld, ldc=Lcp, batch=B * heads, batch_inner=heads,
+               a_str=(Lq * do_ld, dh), b_str=(Lc * v_ld, dh), c_str=(HS, Lq * Lcp), alpha=sign,
+               epilogue=L.EPI_SOFTMAX_BWD, residual=P, ldr=Lcp, r_str=(HS, Lq * Lcp))
+    else:
+        dP = torch.empty(B, heads, Lq, Lcp, device=dO.device, dtype=torch.float32)
+        K.gemm(dO, v, dP, m=Lq, n=Lc, k=dh, lda=do_ld, ldb=v_ld, ldc=Lcp, batch=B * heads, batch_inner=heads,
+               a_str=(Lq * do_ld, dh), b_str=(Lc * v_ld, dh), c_str=(HS, Lq * Lcp), alpha=sign)
+        dS = K.softmax_bwd(P, dP, Lc, 1.0, cd)
+        del dP
     K.gemm(dS, k, dq, m=Lq, n=dh, k=Lc, lda=Lcp, ldb=k_ld, ldc=dq_ld, b_mn=True, batch=B * heads, batch_inner=heads,
            a_str=(HS, Lq * Lcp), b_str=(Lc * k_ld, dh), c_str=(Lq * dq_ld, dh), alpha=alpha)
     K.gemm(dS, q, dk, m=Lc, n=dh, k=Lq, lda=Lcp, ldb=q_ld, ldc=dk_ld, a_mn=True, b_mn=True, batch=B * heads,

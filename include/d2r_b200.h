@@ -34,7 +34,11 @@ typedef enum { D2R_F32 = 0, D2R_BF16 = 1 } d2r_dtype;
 typedef enum { D2R_ACT_NONE = 0, D2R_ACT_RELU = 1, D2R_ACT_TANH = 2 } d2r_act;
 typedef enum {
   D2R_EPI_STD = 0,    /* c = act(alpha*acc + bias) + residual                          */
-  D2R_EPI_SQDIFF = 1  /* d = residual - (alpha*acc + bias);  c2 = d;  c = d*d          */
+  D2R_EPI_SQDIFF = 1, /* d = residual - (alpha*acc + bias);  c2 = d;  c = d*d          */
+  /* Attention scores never leave the SM (bf16 tensor-core path, n <= 256 = one N tile):       */
+  D2R_EPI_SOFTMAX = 2,     /* c = softmax_row(alpha*acc)            SelfAttention.py:33-37,    */
+                           /*                                       XModules.py:306-309        */
+  D2R_EPI_SOFTMAX_BWD = 3  /* c = P * (alpha*acc - sum_row(alpha*acc * P)),  P = residual      */
 } d2r_epilogue;
 
 /* ---- library probes ------------------------------------------------------------------ */

@@ -11,7 +11,7 @@ lds / batch strides), which is exactly what the orchestration can get wrong.
 import torch
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_STD, EPI_SQDIFF = 0, 1
+EPI_STD, EPI_SQDIFF, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2, 3
 
 
 def _view(t, sizes, strides):
@@ -46,6 +46,12 @@ def gemm(a, b, c, *, m, n, k, lda, ldb, ldc, a_mn=False, b_mn=False, batch=1, ba
         d = R - v
         _view(c2, (bo, bi, m, n), (c_str[0], c_str[1], ldc, 1)).copy_(d.to(c2.dtype))
         v = d * d
+    elif epilogue == EPI_SOFTMAX:
+        assert a.dtype == torch.bfloat16 and c.dtype == torch.bfloat16 and n <= 256 and bias is None
+        v = torch.softmax(v, -1)
+    elif epilogue == EPI_SOFTMAX_BWD:
+        assert a.dtype == torch.bfloat16 and c.dtype == torch.bfloat16 and n <= 256 and R is not None
+        v = R * (v - (v * R).sum(-1, keepdim=True))
     else:
         if act_cols:
             v = torch.cat([_act(v[..., :act_cols], act), v[..., act_cols:]], -1)

@@ -123,6 +123,44 @@ def test_epilogues(dtype):
     assert (sq.double() - dref ** 2).abs().max().item() <= 2 * tol * (dref ** 2).abs().max().item() + tol
 
 
+@pytest.mark.parametrize("Lq,Lc,dk,H", [(32, 32, 48, 16), (36, 32, 48, 16), (50, 37, 64, 4), (130, 200, 256, 1),
+                                        (256, 256, 64, 2)])
+def test_softmax_epilogues(Lq, Lc, dk, H):
+    """P = softmax(alpha Q K^T) and dS = P * (alpha dO V^T - rowsum(alpha dO V^T * P)) finished in the GEMM's
+    epilogue (scores never written to HBM); ragged Lc exercises the column mask and the padded ld."""
+    from d2r_b200 import kernels as K
+    from d2r_b200 import _lib as L
+    B = 3
+    Lcp = (Lc + 7) // 8 * 8
+    bf = torch.bfloat16
+    q = torch.randn(B, H, Lq, dk, device="cuda").to(bf)
+    k = torch.randn(B, H, Lc, dk, device="cuda").to(bf)
+    alpha = 1.0 / dk ** 0.5
+    P = torch.full((B, H, Lq, Lcp), float("nan"), device="cuda", dtype=bf)
+    K.gemm(q, k, P, m=Lq, n=Lc, k=dk, lda=dk, ldb=dk, ldc=Lcp, batch=B * H, batch_inner=H,
+           a_str=(H * Lq * dk, Lq * dk), b_str=(H * Lc * dk, Lc * dk), c_str=(H * Lq * Lcp, Lq * Lcp), alpha=alpha,
+           epilogue=L.EPI_SOFTMAX)
+    ref = torch.softmax(alpha * q.double() @ k.double().transpose(-1, -2), -1)
+    assert torch.isfinite(P[..., :Lc]).all()
+    assert (P[..., :Lc].double() - ref).abs().max().item() <= 8e-3
+    assert (P[..., :Lc].double().sum(-1) - 1).abs().max().item() <= 2e-2
+    do = torch.randn(B, H, Lq, dk, device="cuda").to(bf)
+    v = torch.randn(B, H, Lc, dk, device="cuda").to(bf)
+    dS = torch.full((B, H, Lq, Lcp), float("nan"), device="cuda", dtype=bf)
+    K.gemm(do, v, dS, m=Lq, n=Lc, k=dk, lda=dk, ldb=dk, ldc=Lcp, batch=B * H, batch_inner=H,
+           a_str=(H * Lq * dk, Lq * dk), b_str=(H * Lc * dk, Lc * dk), c_str=(H * Lq * Lcp, Lq * Lcp), alpha=-0.5,
+           epilogue=L.EPI_SOFTMAX_BWD, residual=P, ldr=Lcp, r_str=(H * Lq * Lcp, Lq * Lcp))
+    Pd = P[..., :Lc].double()
+    dP = -0.5 * do.double() @ v.double().transpose(-1, -2)
+    ref = Pd * (dP - (dP * Pd).sum(-1, keepdim=True))
+    assert (dS[..., :Lc].double() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    # the fp32 path has no fused softmax
+    with pytest.raises(RuntimeError):
+        K.gemm(q.float(), k.float(), P, m=Lq, n=Lc, k=dk, lda=dk, ldb=dk, ldc=Lcp, batch=B * H, batch_inner=H,
+               a_str=(H * Lq * dk, Lq * dk), b_str=(H * Lc * dk, Lc * dk), c_str=(H * Lq * Lcp, Lq * Lcp),
+               epilogue=L.EPI_SOFTMAX)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_wgrad_split_k(dtype):
     """dW[n,k] = dY^T X: both operands MN-major, contraction over the long row dimension, split-K."""

@@ -40,7 +40,11 @@ def test_state_dict_and_seeded_init_match_reference(branch):
 
 
 def test_signatures_match_reference():
-    from d2r_b200.interaction import Cells, DynamicInteraction, InteractionModule, Refinement, Router, SelfAttention, XModules
+    import importlib
+    from d2r_b200.interaction import Cells, DynamicInteraction, Refinement, Router, SelfAttention, XModules
+    # the package re-exports the InteractionModule CLASS under the submodule's name, as `from models.InteractionModule
+    # import InteractionModule` does in the reference; fetch the submodule itself explicitly
+    InteractionModule = importlib.import_module("d2r_b200.interaction.InteractionModule")
     sig = lambda f: list(inspect.signature(f).parameters)
     assert sig(InteractionModule.InteractionModule.__init__) == ["self", "args", "num_layer_routing", "num_cells", "path_hid"]
     assert sig(InteractionModule.InteractionModule.forward)[:3] == ["self", "text", "image"]
