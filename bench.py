@@ -188,7 +188,7 @@ def own_arm(args):
     import torch.distributed as dist
     from d2r_b200 import kernels as K
     from d2r_b200.dp import GradAllReducer
-    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule, run_pair
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,15 +216,19 @@ def own_arm(args):
         d_text.copy_(h_text)
         d_image.copy_(h_image)
 
-    def fwd_bwd():
+    def fwd_bwd(serial=args.serial_branches):
         d_text.grad = None
         d_image.grad = None
         for m in (mt, mi):
             for p in m.parameters():
                 p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            o1, s1 = mt(d_text, d_image)
-            o2, s2 = mi(d_text, d_image)
+            if serial:
+                o1, s1 = mt(d_text, d_image)
+                o2, s2 = mi(d_text, d_image)
+            else:
+                # the two branch stacks of modeling_unimo.py:842-843, issued on two CUDA streams
+                (o1, s1), (o2, s2) = run_pair(mt, mi, d_text, d_image)
         loss = o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()
         loss.backward()
         return loss
@@ -325,7 +329,8 @@ def own_arm(args):
         launches = eager_launches_per_step * args.steps
 
     # --- per-kernel roofline pass (separate, eager, CUDA events around every C-ABI GEMM launch) -----
-    roof, hbm = kernel_roofline(fwd_bwd, K, torch) if rank == 0 else (None, None)
+    # (branches back to back here: kernels of concurrent streams would overlap inside each other's event pairs)
+    roof, hbm = kernel_roofline(lambda: fwd_bwd(serial=True), K, torch) if rank == 0 else (None, None)
 
     if rank == 0:
         peaks = {}
@@ -351,7 +356,8 @@ def own_arm(args):
             "metric": "routed-interaction samples/sec fwd+bwd", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world) | {"cuda_graph": graph is not None},
+            "config": workload_config(world) | {"cuda_graph": graph is not None,
+                                                  "branch_streams": 1 if args.serial_branches else 2},
             "clocks": clocks,
             "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": (h_text.numel() + h_image.numel()) * 4, "d2h_bytes_per_step": 4,
@@ -437,6 +443,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--serial-branches", action="store_true",
+                    help="call the two branch modules back to back instead of run_pair (two CUDA streams)")
     ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

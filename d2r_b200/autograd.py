@@ -10,6 +10,7 @@ given bf16 inputs, fp32 arithmetic otherwise -- the two modes the reference supp
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -35,42 +36,113 @@ def _stager_of(module: torch.nn.Module) -> S.Stager:
     return st
 
 
-class _BlockFn(torch.autograd.Function):
+def _fwd_one(spec, tensors):
+    """Run one block's forward on the CURRENT stream -> (outs, record for the backward)."""
+    n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = spec
+    inputs = tensors[:n_in]
+    P: Dict[str, Tensor] = dict(zip(names, tensors[n_in:]))
+    P.update(bufs)
+    env = S.Env(P, cd, training, stager, heads)
+    x_cd = [None if t is None else t.detach().to(cd).contiguous() for t in inputs]
+    outs, state = fwd(env, x_cd)
+    rec = dict(spec=spec, state=state, in_dtypes=[None if t is None else t.dtype for t in inputs],
+               out_meta=[(o.shape, o.dtype) for o in outs])
+    return tuple(outs), rec
+
+
+def _bwd_one(rec, grads) -> List[Optional[Tensor]]:
+    """Run one block's backward on the CURRENT stream -> [input grads..., parameter grads...]."""
+    n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = rec["spec"]
+    # parameters are only needed by name -> the forward's tensors are reachable through the state's env
+    env: S.Env = rec["state"]["env"]
+    env.G = {}
+    gs = []
+    for g, (shape, dtype) in zip(grads, rec["out_meta"]):
+        gs.append(None if g is None else g.to(dtype).contiguous())
+    in_grads = bwd(env, rec["state"], gs)
+    rec["state"] = None
+    res: List[Optional[Tensor]] = []
+    for g, dt in zip(in_grads, rec["in_dtypes"]):
+        res.append(None if (g is None or dt is None) else g.to(dt))
+    for nme in names:
+        res.append(env.G.get(nme))
+    return res
+
+
+class _Lanes:
+    """Fork/join of n concurrent blocks: block 0 stays on the caller's stream, block i > 0 runs on a cached side
+    stream that first waits for the caller's stream; join() makes the caller's stream wait for all of them.
+    The pattern is capturable in a CUDA graph (the side streams fork from and join into the capturing stream)."""
+
+    _side: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+
+    def __init__(self, device: torch.device, n: int):
+        self.cur = torch.cuda.current_stream(device) if n > 1 else None
+        self.streams = [self.cur]
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        for i in range(1, n):
+            key = (idx, i)
+            if key not in _Lanes._side:
+                _Lanes._side[key] = torch.cuda.Stream(device=device)
+            self.streams.append(_Lanes._side[key])
+        # fork NOW, before block 0 puts any work on the caller's stream: a later wait would order the side
+        # streams behind block 0 and serialise everything
+        for st in self.streams[1:]:
+            st.wait_stream(self.cur)
+
+    def lane(self, i: int):
+        """Context manager under which block i is issued."""
+        if i == 0:
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self.streams[i])
+
+    def join(self) -> None:
+        for st in self.streams[1:]:
+            self.cur.wait_stream(st)
+
+
+class _BlocksFn(torch.autograd.Function):
+    """N independent blocks as ONE autograd node.  With N > 1 the blocks are issued on separate CUDA streams:
+    their kernels fill each other's partial waves and sub-148-CTA launches.  Each lane allocates its temporaries
+    while its own stream is current, every fork waits on the caller's stream and every call joins before it
+    returns, so no block of memory is reused across lanes without an ordering edge."""
+
+    last_out_counts: List[int] = []
+
     @staticmethod
-    def forward(ctx, spec, *tensors):
-        n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = spec
-        inputs = tensors[:n_in]
-        P: Dict[str, Tensor] = dict(zip(names, tensors[n_in:]))
-        P.update(bufs)
-        env = S.Env(P, cd, training, stager, heads)
-        x_cd = [None if t is None else t.detach().to(cd).contiguous() for t in inputs]
-        outs, state = fwd(env, x_cd)
-        ctx.spec = spec
-        ctx.state = state
-        ctx.in_dtypes = [None if t is None else t.dtype for t in inputs]
-        ctx.out_meta = [(o.shape, o.dtype) for o in outs]
-        nd = [outs[i] for i in out_nondiff]
+    def forward(ctx, specs, *tensors):
+        dev = next(t.device for t in tensors if t is not None)
+        lanes = _Lanes(dev, len(specs))
+        recs, all_outs, off = [], [], 0
+        for i, spec in enumerate(specs):
+            n = spec[0] + len(spec[1])
+            with lanes.lane(i):
+                outs, rec = _fwd_one(spec, tensors[off:off + n])
+            off += n
+            recs.append(rec)
+            all_outs.append(outs)
+        lanes.join()
+        ctx.recs = recs
+        ctx.dev = dev
+        _BlocksFn.last_out_counts = [len(o) for o in all_outs]
+        nd = [outs[j] for outs, spec in zip(all_outs, specs) for j in spec[9]]
         if nd:
             ctx.mark_non_differentiable(*nd)
-        return tuple(outs)
+        return tuple(o for outs in all_outs for o in outs)
 
     @staticmethod
     def backward(ctx, *grads):
-        n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = ctx.spec
-        P: Dict[str, Tensor] = {}
-        # parameters are only needed by name -> the forward's tensors are reachable through the state's env
-        env: S.Env = ctx.state["env"]
-        env.G = {}
-        gs = []
-        for g, (shape, dtype) in zip(grads, ctx.out_meta):
-            gs.append(None if g is None else g.to(dtype).contiguous())
-        in_grads = bwd(env, ctx.state, gs)
-        ctx.state = None
+        recs = ctx.recs
+        lanes = _Lanes(ctx.dev, len(recs))
         res: List[Optional[Tensor]] = [None]
-        for g, dt in zip(in_grads, ctx.in_dtypes):
-            res.append(None if (g is None or dt is None) else g.to(dt))
-        for nme in names:
-            res.append(env.G.get(nme))
+        off = 0
+        for i, rec in enumerate(recs):
+            n = len(rec["out_meta"])
+            with lanes.lane(i):
+                res += _bwd_one(rec, grads[off:off + n])
+            off += n
+        lanes.join()
+        ctx.recs = None
         return tuple(res)
 
 
@@ -81,11 +153,9 @@ def _require_cuda(inputs) -> None:
                                "there is no CPU path")
 
 
-def run_block(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]],
-              fwd: Callable, bwd: Callable, *, prefix: str = "", cd: Optional[torch.dtype] = None,
-              heads: int = 16, out_nondiff: Tuple[int, ...] = ()) -> Tuple[Tensor, ...]:
-    """See module docstring.  ``prefix`` is prepended to the module's parameter names so that helper
-    code written against full stack names (e.g. 'L.glac.fc_1') can serve a stand-alone sub-module."""
+def _make_spec(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]], fwd: Callable, bwd: Callable, *,
+               prefix: str = "", cd: Optional[torch.dtype] = None, heads: int = 16,
+               out_nondiff: Tuple[int, ...] = ()):
     _require_cuda(inputs)
     cd = cd or compute_dtype(*inputs)
     names, params = [], []
@@ -102,4 +172,31 @@ def run_block(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]],
 
     spec = (len(inputs), tuple(names), bufs, fwd_wrapped, bwd, cd, module.training, _stager_of(module), heads,
             tuple(out_nondiff))
-    return _BlockFn.apply(spec, *inputs, *params)
+    return spec, list(inputs) + params
+
+
+def run_block(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]],
+              fwd: Callable, bwd: Callable, *, prefix: str = "", cd: Optional[torch.dtype] = None,
+              heads: int = 16, out_nondiff: Tuple[int, ...] = ()) -> Tuple[Tensor, ...]:
+    """See module docstring.  ``prefix`` is prepended to the module's parameter names so that helper
+    code written against full stack names (e.g. 'L.glac.fc_1') can serve a stand-alone sub-module."""
+    spec, tensors = _make_spec(module, inputs, fwd, bwd, prefix=prefix, cd=cd, heads=heads, out_nondiff=out_nondiff)
+    return _BlocksFn.apply((spec,), *tensors)
+
+
+def run_blocks(requests: Sequence[dict]) -> List[Tuple[Tensor, ...]]:
+    """Several independent blocks (each a dict of run_block's arguments) as one autograd node, issued on
+    concurrent CUDA streams.  Returns one output tuple per request."""
+    specs, tensors = [], []
+    for rq in requests:
+        rq = dict(rq)
+        spec, ts = _make_spec(rq.pop("module"), rq.pop("inputs"), rq.pop("fwd"), rq.pop("bwd"), **rq)
+        specs.append(spec)
+        tensors += ts
+    flat = _BlocksFn.apply(tuple(specs), *tensors)
+    # split by each block's number of outputs: not known before the forward ran, so the forward reports it
+    res, off = [], 0
+    for n in _BlocksFn.last_out_counts:
+        res.append(tuple(flat[off:off + n]))
+        off += n
+    return res

@@ -9,12 +9,12 @@ from ``stack.stack_forward`` / ``stack.stack_backward``.  ``num_layer_routing >=
 import torch.nn as nn
 
 from .. import stack as S
-from ..autograd import run_block
+from ..autograd import run_block, run_blocks
 from .DynamicInteraction import (DynamicInteraction_Layer, DynamicInteraction_Layer0,
                                  Reversed_DynamicInteraction_Layer, Reversed_DynamicInteraction_Layer0)
 
 
-def _stack_call(mod, own, ctx, want_probs=False):
+def _stack_request(mod, own, ctx):
     R, Kc = mod.num_layer_routing, mod.num_cells
     heads = mod.dynamic_itr_l0.imrc.sa.h
 
@@ -28,11 +28,33 @@ def _stack_call(mod, own, ctx, want_probs=False):
                                   d_probs if any(g is not None for g in d_probs) else None)
         return dx, dz
 
-    res = run_block(mod, [own, ctx], fwd, bwd, heads=heads)
+    return dict(module=mod, inputs=[own, ctx], fwd=fwd, bwd=bwd, heads=heads)
+
+
+def _stack_result(mod, res, want_probs):
     mod.last_path_probs = [p.detach() for p in res[2:]]   # per-layer routing probabilities (inspection only)
     if want_probs:
         return [res[0]], res[1], list(res[2:])
     return [res[0]], res[1]
+
+
+def _stack_call(mod, own, ctx, want_probs=False):
+    return _stack_result(mod, run_block(**_stack_request(mod, own, ctx)), want_probs)
+
+
+def run_pair(itr_module, reversed_itr_module, text, image, return_path_probs=False):
+    """Both branch stacks of one batch, concurrently.  Replaces the reference's back-to-back calls
+    (models/modeling_unimo.py:842-843)
+
+        sim_mat, sim_paths = self.itr_module(text, image)
+        Reversed_sim_mat, Reversed_sim_paths = self.Reversed_itr_module(text, image)
+
+    with ``(sim_mat, sim_paths), (Reversed_sim_mat, Reversed_sim_paths) = run_pair(self.itr_module,
+    self.Reversed_itr_module, text, image)``.  The two stacks are independent until the loss, so they are
+    issued on two CUDA streams inside one autograd node (forward and backward): on B200 the tail waves and the
+    many small launches of one stack are filled by the other.  Results are identical to the two separate calls."""
+    rt, ri = run_blocks([_stack_request(itr_module, text, image), _stack_request(reversed_itr_module, image, text)])
+    return _stack_result(itr_module, rt, return_path_probs), _stack_result(reversed_itr_module, ri, return_path_probs)
 
 
 class InteractionModule(nn.Module):

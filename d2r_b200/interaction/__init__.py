@@ -6,4 +6,4 @@ order (so ``state_dict`` round-trips and the same seed gives the same initial we
 the arithmetic runs in ``libd2r_b200.so``.  See INTEGRATION.md for the two-line shim that makes the
 reference's ``modeling_unimo.py`` import these instead of its own.
 """
-from .InteractionModule import InteractionModule, Reversed_InteractionModule  # noqa: F401
+from .InteractionModule import InteractionModule, Reversed_InteractionModule, run_pair  # noqa: F401

@@ -42,18 +42,28 @@ class _ZeroArena:
         return v
 
 
-_zero_arena = _ZeroArena()
+# one arena per CUDA stream: a chunk is zeroed on the stream that is current when it is taken, so it must only
+# be handed to kernels launched on that same stream (concurrent blocks run on different streams)
+_zero_arenas: dict = {}
+
+
+def _arena() -> _ZeroArena:
+    key = L.stream()
+    a = _zero_arenas.get(key)
+    if a is None:
+        a = _zero_arenas[key] = _ZeroArena()
+    return a
 
 
 def zeros_f32(shape, device: torch.device) -> Tensor:
     n = 1
     for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
         n *= int(d)
-    return _zero_arena.take(n, device).view(shape)
+    return _arena().take(n, device).view(shape)
 
 
 def zero_arena_reset() -> None:
-    _zero_arena.reset()
+    _arena().reset()
 
 
 def gemm(a: Tensor, b: Tensor, c: Tensor, *, m: int, n: int, k: int, lda: int, ldb: int, ldc: int,

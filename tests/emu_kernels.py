@@ -280,3 +280,11 @@ def saf_bwd(d_out, sg, sl, w, bias, bn_w, bn_b, rm, rv, training, saved):
     out.backward(d_out)
     g = [t.grad if t.grad is not None else torch.zeros_like(t) for t in leaves]
     return g[0].to(sg.dtype), g[1].to(sl.dtype), g[2], g[3], g[4], g[5]
+
+
+def zeros_f32(shape, device):
+    return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
+def zero_arena_reset():
+    pass

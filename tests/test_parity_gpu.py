@@ -203,3 +203,69 @@ def test_cpu_tensors_are_rejected():
     text, image = O.make_inputs(11, 2, 8, 5)
     with pytest.raises(RuntimeError):
         m(text, image)
+
+
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
+def test_run_pair_equals_back_to_back_calls(bf16, graph):
+    """run_pair issues the two branch stacks on two CUDA streams (one autograd node); the results must be the
+    ones of the reference's back-to-back calls (modeling_unimo.py:842-843).  Forward values are bit-identical;
+    gradients that are accumulated with atomics (split-K, column sums) agree to rounding."""
+    from d2r_b200.interaction import run_pair
+    R, Kc = 3, 6
+    mt = build(R, Kc, False, O.make_params(PARAM_SEED_BASE + 1, R, Kc), training=True)
+    mi = build(R, Kc, True, O.make_params(PARAM_SEED_BASE + 2, R, Kc), training=True)
+    text, image = O.make_inputs(INPUT_SEED_BASE + 6, 6, 24, 13, realistic=True)
+    t = text.cuda().requires_grad_(True)
+    i = image.cuda().requires_grad_(True)
+    ctx = lambda: torch.autocast("cuda", dtype=torch.bfloat16) if bf16 else torch.autocast("cuda", enabled=False)
+
+    def step(pair):
+        t.grad = None
+        i.grad = None
+        for m in (mt, mi):
+            for p in m.parameters():
+                p.grad = None
+        with ctx():
+            if pair:
+                (o1, s1), (o2, s2) = run_pair(mt, mi, t, i)
+            else:
+                o1, s1 = mt(t, i)
+                o2, s2 = mi(t, i)
+        (o1[0].sum() + 2 * s1.sum() + 3 * o2[0].sum() + s2.sum()).backward()
+        return [o1[0], s1, o2[0], s2]
+
+    def snapshot(outs):
+        vals = [o.detach().clone() for o in outs] + [t.grad.clone(), i.grad.clone()]
+        grads = {(b, k): p.grad.clone() for b, m in (("t", mt), ("i", mi)) for k, p in m.named_parameters()
+                 if p.grad is not None}
+        return vals, grads
+
+    ref_vals, ref_grads = snapshot(step(False))
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(True)                                   # warm-up outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = step(True)
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+    else:
+        outs = step(True)
+    vals, grads = snapshot(outs)
+    for a, b in zip(vals[:4], ref_vals[:4]):
+        assert torch.equal(a, b)
+    tol = 2e-2 if bf16 else 1e-5
+    for a, b in zip(vals[4:], ref_vals[4:]):
+        assert relerr(a, b) <= tol
+    assert grads.keys() == ref_grads.keys()
+    for k in grads:
+        if O.is_zero_grad_param(k[1], True):
+            continue                       # mathematically zero: both sides hold rounding noise only
+        scale = ref_grads[k].abs().max().item()
+        assert (grads[k] - ref_grads[k]).abs().max().item() <= tol * scale + 1e-6, k

@@ -27,6 +27,19 @@ def emulated(monkeypatch):
         if not name.startswith("_") and callable(getattr(E, name)) and hasattr(K, name):
             monkeypatch.setattr(K, name, getattr(E, name))
     monkeypatch.setattr(A, "_require_cuda", lambda inputs: None)
+
+    class _NoLanes:                      # no CUDA streams on the CPU: concurrent blocks run one after the other
+        def __init__(self, device, n):
+            pass
+
+        def lane(self, i):
+            import contextlib
+            return contextlib.nullcontext()
+
+        def join(self):
+            pass
+
+    monkeypatch.setattr(A, "_Lanes", _NoLanes)
     yield
 
 
@@ -177,3 +190,34 @@ def test_emulated_bf16_mode(emulated):
     # loose: bf16 activations + the cancellation in the normalised routing probabilities (sum_j P_ij = 1)
     # make individual gradients noisy; exact gradient parity is asserted in the fp32 mode above
     assert worst[0][1] < 0.6, worst
+
+
+def test_emulated_run_pair_equals_separate_calls(emulated):
+    """run_pair (both branch stacks as one autograd node) == the reference's two back-to-back module calls."""
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule, run_pair
+    torch.manual_seed(5)
+    mt = InteractionModule(make_args(), 3, 6, 128)
+    mi = Reversed_InteractionModule(make_args(), 3, 6, 128)
+    text0, image0 = O.make_inputs(INPUT_SEED_BASE + 3, 3, 9, 7, realistic=True)
+
+    def run(pair):
+        for m in (mt, mi):
+            m.zero_grad(set_to_none=True)
+        text, image = text0.clone().requires_grad_(True), image0.clone().requires_grad_(True)
+        if pair:
+            (o1, s1), (o2, s2) = run_pair(mt, mi, text, image)
+        else:
+            o1, s1 = mt(text, image)
+            o2, s2 = mi(text, image)
+        (o1[0].sum() + 2 * s1.sum() + 3 * o2[0].sum() + s2.sum()).backward()
+        grads = {("t", k): p.grad.clone() for k, p in mt.named_parameters() if p.grad is not None}
+        grads.update({("i", k): p.grad.clone() for k, p in mi.named_parameters() if p.grad is not None})
+        return [o1[0], s1, o2[0], s2, text.grad, image.grad], grads
+
+    a, ga = run(False)
+    b, gb = run(True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert ga.keys() == gb.keys()
+    for k in ga:
+        assert torch.equal(ga[k], gb[k]), k

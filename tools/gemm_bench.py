@@ -28,6 +28,14 @@ CASES = {
     "fwd_wide": (32768, 4608, 768, False, False, dict(bias=True, out="bf16")),
     "fwd_longk": (32768, 768, 4608, False, False, dict(out="bf16")),
     "small_tc": (256, 768, 768, False, False, dict(bias=True, out="f32")),
+    "small_tc_bn128": (256, 768, 768, False, False, dict(bias=True, out="f32", tile_n=128)),
+    "small_tc_bn64": (256, 768, 768, False, False, dict(bias=True, out="f32", tile_n=64)),
+    "small_dgrad_bn64": (256, 768, 768, False, True, dict(out="f32", tile_n=64)),
+    "small_wgrad": (768, 768, 256, True, True, dict(out="f32")),
+    "small_wgrad_bn64": (768, 768, 256, True, True, dict(out="f32", tile_n=64)),
+    "img_dgrad": (12800, 768, 768, False, True, dict(out="bf16")),
+    "img_dgrad_bn192": (12800, 768, 768, False, True, dict(out="bf16", tile_n=192)),
+    "fwd_res_bn192": (32768, 768, 768, False, False, dict(bias=True, out="bf16", residual=True, act=L.ACT_RELU, tile_n=192)),
     "small_f32": (256, 768, 768, False, False, dict(bias=True, out="f32", f32=True)),
 }
 
