@@ -190,6 +190,9 @@ def own_arm(args):
     from d2r_b200.dp import GradAllReducer
     from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule, run_pair
 
+    import d2r_b200.lanes as LN
+    if args.cell_lanes is not None:
+        LN.CELL_LANES = max(1, args.cell_lanes)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -357,7 +360,8 @@ def own_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world) | {"cuda_graph": graph is not None,
-                                                  "branch_streams": 1 if args.serial_branches else 2},
+                                                  "branch_streams": 1 if args.serial_branches else 2,
+                                                  "cell_lanes": LN.CELL_LANES},
             "clocks": clocks,
             "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": (h_text.numel() + h_image.numel()) * 4, "d2h_bytes_per_step": 4,
@@ -445,6 +449,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--serial-branches", action="store_true",
                     help="call the two branch modules back to back instead of run_pair (two CUDA streams)")
+    ap.add_argument("--cell-lanes", type=int, default=None,
+                    help="CUDA streams per routing layer (default: d2r_b200.lanes.CELL_LANES; 1 = one stream)")
     ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -10,11 +10,11 @@ given bf16 inputs, fp32 arithmetic otherwise -- the two modes the reference supp
 """
 from __future__ import annotations
 
-import contextlib
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from . import lanes as LN
 from . import stack as S
 
 Tensor = torch.Tensor
@@ -69,38 +69,6 @@ def _bwd_one(rec, grads) -> List[Optional[Tensor]]:
     return res
 
 
-class _Lanes:
-    """Fork/join of n concurrent blocks: block 0 stays on the caller's stream, block i > 0 runs on a cached side
-    stream that first waits for the caller's stream; join() makes the caller's stream wait for all of them.
-    The pattern is capturable in a CUDA graph (the side streams fork from and join into the capturing stream)."""
-
-    _side: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
-
-    def __init__(self, device: torch.device, n: int):
-        self.cur = torch.cuda.current_stream(device) if n > 1 else None
-        self.streams = [self.cur]
-        idx = device.index if device.index is not None else torch.cuda.current_device()
-        for i in range(1, n):
-            key = (idx, i)
-            if key not in _Lanes._side:
-                _Lanes._side[key] = torch.cuda.Stream(device=device)
-            self.streams.append(_Lanes._side[key])
-        # fork NOW, before block 0 puts any work on the caller's stream: a later wait would order the side
-        # streams behind block 0 and serialise everything
-        for st in self.streams[1:]:
-            st.wait_stream(self.cur)
-
-    def lane(self, i: int):
-        """Context manager under which block i is issued."""
-        if i == 0:
-            return contextlib.nullcontext()
-        return torch.cuda.stream(self.streams[i])
-
-    def join(self) -> None:
-        for st in self.streams[1:]:
-            self.cur.wait_stream(st)
-
-
 class _BlocksFn(torch.autograd.Function):
     """N independent blocks as ONE autograd node.  With N > 1 the blocks are issued on separate CUDA streams:
     their kernels fill each other's partial waves and sub-148-CTA launches.  Each lane allocates its temporaries
@@ -112,7 +80,7 @@ class _BlocksFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, specs, *tensors):
         dev = next(t.device for t in tensors if t is not None)
-        lanes = _Lanes(dev, len(specs))
+        lanes = LN.fork(dev, len(specs), "blocks")
         recs, all_outs, off = [], [], 0
         for i, spec in enumerate(specs):
             n = spec[0] + len(spec[1])
@@ -133,7 +101,7 @@ class _BlocksFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         recs = ctx.recs
-        lanes = _Lanes(ctx.dev, len(recs))
+        lanes = LN.fork(ctx.dev, len(recs), "blocks")
         res: List[Optional[Tensor]] = [None]
         off = 0
         for i, rec in enumerate(recs):

@@ -63,7 +63,9 @@ def zeros_f32(shape, device: torch.device) -> Tensor:
 
 
 def zero_arena_reset() -> None:
-    _arena().reset()
+    """Start of a backward pass: drop every stream's arena so that the chunks this pass uses are zeroed inside
+    it (a CUDA graph of the pass must contain the memsets).  Views handed out earlier keep their chunk alive."""
+    _zero_arenas.clear()
 
 
 def gemm(a: Tensor, b: Tensor, c: Tensor, *, m: int, n: int, k: int, lda: int, ldb: int, ldc: int,

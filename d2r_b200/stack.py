@@ -28,6 +28,7 @@ import torch
 
 from . import _lib as L
 from . import kernels as K
+from . import lanes as LN
 
 Tensor = torch.Tensor
 CELLS6 = ("ric", "glac", "imrc", "cmrc", "crcmc", "gesc")   # emb_lst order, DynamicInteraction.py:41-48
@@ -536,20 +537,33 @@ def layer_forward(env: Env, pre: str, xs: Sequence[Tensor], z: Tensor, pooled: T
     cells = CELLS6[:Kc]
     n_out = 1 if final else Kc
     routers = [f"{pre}.{cn}.router" for cn in cells]
-    norm, gate, rsv = _routers_fwd(env, routers, pooled, n_out, final)
+    # The cells read the same layer input and are independent until the aggregation: one lane (CUDA stream)
+    # each for the three token-level cells, lane 0 (the caller's stream) for the K/V projections they share,
+    # the routers and the two [B,D] global cells.
+    lanes = LN.fork(z.device, LN.CELL_LANES if LN.FWD_LANES else 1, "cells")
+    with lanes.lane(1):
+        imrc_out, imrc_sv = _imrc_fwd(env, pre + ".imrc.sa", xs[2])
     kv = _KV(env, z, [pre + ".glac.CrossModalAlignment", pre + ".cmrc.refine.CrossModalAlignment"] +
              ([pre + ".crcmc.CrossModalAlignment"] if Kc > 4 else []))
-    st = dict(xs=list(xs), z=z, kv=kv, router=rsv, norm=norm, gate=gate, final=final, Kc=Kc)
+    lanes.catch_up(2)
+    with lanes.lane(2):
+        cmrc_out, cmrc_sv = _cmrc_fwd(env, pre + ".cmrc.refine", xs[3], kv, 1)
+    if Kc > 4:
+        lanes.catch_up(3)
+        with lanes.lane(3):
+            crcmc_out, crcmc_sv = _crcmc_fwd(env, pre + ".crcmc", xs[4], kv, 2)
+    norm, gate, rsv = _routers_fwd(env, routers, pooled, n_out, final)
+    st = dict(xs=list(xs), z=z, kv=kv, router=rsv, norm=norm, gate=gate, final=final, Kc=Kc, imrc=imrc_sv,
+              cmrc=cmrc_sv)
     glac_out, st["glac"] = _glac_fwd(env, pre + ".glac", xs[1], z, kv, 0)
-    imrc_out, st["imrc"] = _imrc_fwd(env, pre + ".imrc.sa", xs[2])
-    cmrc_out, st["cmrc"] = _cmrc_fwd(env, pre + ".cmrc.refine", xs[3], kv, 1)
     full: List[Optional[Tensor]] = [xs[0], None, imrc_out, cmrc_out]
     bvec: List[Optional[Tensor]] = [None, glac_out, None, None]
     if Kc > 4:
-        crcmc_out, st["crcmc"] = _crcmc_fwd(env, pre + ".crcmc", xs[4], kv, 2)
+        st["crcmc"] = crcmc_sv
         gesc_out, st["gesc"] = _gesc_fwd(env, pre + ".gesc", xs[5], z)
         full += [crcmc_out, None]
         bvec += [None, gesc_out]
+    lanes.join()
     st["full"], st["bvec"] = full, bvec
     outs, pooled_next = K.aggregate_fwd(full, bvec, norm, gate, final, inputs=list(xs) if final else None)
     return outs, pooled_next, norm, st
@@ -564,36 +578,49 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     d_full, d_bvec, dP = K.aggregate_bwd(st["full"], st["bvec"], st["norm"], st["gate"], final, d_outs,
                                          d_pooled_next, inputs=list(xs) if final else None)
     d_norm = dP if d_norm_extra is None else K.axpby(dP, d_norm_extra.contiguous(), 1.0, 1.0)
-    d_pooled = _routers_bwd(env, [f"{pre}.{cn}.router" for cn in cells], st["router"], d_norm, final)
 
     # the row-0 (CLS pooler) gradients of the context are collected in a zero-initialised dz_rows and
     # folded into dz by the key/value projection backward (residual)
     dz_rows = torch.zeros_like(z) if dz_acc is None else dz_acc
+    kv.grads()                                       # allocated on the caller's stream, before the fork
     d_xs: List[Optional[Tensor]] = [None] * Kc
+    # same lanes as the forward (a cell's saved activations were allocated on its lane): the token-level cells
+    # run concurrently, lane 0 takes the routers' backward, GLAC and GESC (both touch row 0 of dz_rows)
+    lanes = LN.fork(z.device, LN.CELL_LANES if LN.BWD_LANES else 1, "cells")
+    with lanes.lane(1):
+        d_xs[2] = _imrc_bwd(env, pre + ".imrc.sa", xs[2], st["imrc"], d_full[2], None)
+    with lanes.lane(2):
+        d_xs[3] = _cmrc_bwd(env, pre + ".cmrc.refine", xs[3], kv, 1, st["cmrc"], d_full[3], None)
+    if Kc > 4:
+        with lanes.lane(3):
+            d_xs[4] = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], None)
+    d_pooled = _routers_bwd(env, [f"{pre}.{cn}.router" for cn in cells], st["router"], d_norm, final)
     if shared_input:
-        acc = d_full[0]
-        acc = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], acc, dz_rows)
-        acc = _imrc_bwd(env, pre + ".imrc.sa", xs[2], st["imrc"], d_full[2], acc)
-        acc = _cmrc_bwd(env, pre + ".cmrc.refine", xs[3], kv, 1, st["cmrc"], d_full[3], acc)
+        # one input tensor feeds every cell: GLAC folds the RIC gradient in as its residual, GESC adds its
+        # row-0 gradient on top, the other cells' gradients are summed after the join
+        acc = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], d_full[0], dz_rows)
         if Kc > 4:
-            acc = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], acc)
             _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], acc, dz_rows)
+        lanes.join()
+        for j in range(2, min(Kc, 5)):
+            acc = K.axpby(acc, d_xs[j], 1.0, 1.0)
         d_xs = [acc]
     else:
         d_xs[0] = d_full[0]
         d_xs[1] = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], None, dz_rows)
-        d_xs[2] = _imrc_bwd(env, pre + ".imrc.sa", xs[2], st["imrc"], d_full[2], None)
-        d_xs[3] = _cmrc_bwd(env, pre + ".cmrc.refine", xs[3], kv, 1, st["cmrc"], d_full[3], None)
         acc_mask = 0b1110
         if Kc > 4:
-            d_xs[4] = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], None)
             d_xs[5] = torch.empty_like(xs[5]) if final else torch.zeros_like(xs[5])
             acc_mask = 0b011110                      # cell 5 (GESC) has no full-size gradient yet: overwrite
+            if not final:
+                _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d_xs[5], dz_rows)
+        lanes.join()
         if final:
             # gated skip of the final layer (DynamicInteraction.py:108-111): touches only gated samples
             K.gate_skip_bwd(d_outs[0], st["norm"], st["gate"], d_xs, acc_mask)
-        if Kc > 4:
-            _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d_xs[5], dz_rows)
+            if Kc > 4:
+                _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d_xs[5], dz_rows)
+    del d_full, d_bvec                               # (kept alive until the join: read by the side lanes)
     dz = kv.backward(env, dz_rows)
     return d_xs, d_pooled, dz
 

@@ -241,7 +241,12 @@ def test_run_pair_equals_back_to_back_calls(bf16, graph):
                  if p.grad is not None}
         return vals, grads
 
-    ref_vals, ref_grads = snapshot(step(False))
+    import d2r_b200.lanes as LN
+    LN.ENABLED = False                                   # reference: every launch on one stream
+    try:
+        ref_vals, ref_grads = snapshot(step(False))
+    finally:
+        LN.ENABLED = True
     if graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -252,7 +257,7 @@ def test_run_pair_equals_back_to_back_calls(bf16, graph):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             outs = step(True)
-        for _ in range(2):
+        for _ in range(4):
             g.replay()
         torch.cuda.synchronize()
     else:

@@ -28,18 +28,8 @@ def emulated(monkeypatch):
             monkeypatch.setattr(K, name, getattr(E, name))
     monkeypatch.setattr(A, "_require_cuda", lambda inputs: None)
 
-    class _NoLanes:                      # no CUDA streams on the CPU: concurrent blocks run one after the other
-        def __init__(self, device, n):
-            pass
-
-        def lane(self, i):
-            import contextlib
-            return contextlib.nullcontext()
-
-        def join(self):
-            pass
-
-    monkeypatch.setattr(A, "_Lanes", _NoLanes)
+    import d2r_b200.lanes as LN
+    monkeypatch.setattr(LN, "ENABLED", False)   # no CUDA streams on the CPU
     yield
 
 
