@@ -1,6 +1,8 @@
 // HBM-bound elementwise / row-reduction kernels of the cells: dtype casts, activation
 // backward + bias gradient, row softmax, row L2-norm, FiLM modulation, squared-difference
 // backward, GESC gate.  All use 16-byte vector accesses on the contiguous dimension.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -80,12 +82,13 @@ template <> struct Raw8<float> {
 template <typename T, bool ACT>
 __global__ void __launch_bounds__(kThreads) bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y,
                                                                 int act, T* __restrict__ dz, float* __restrict__ db,
-                                                                long long rows, int cols, long long ld) {
+                                                                long long rows, int cols, long long ld,
+                                                                int rows_per_block) {
   __shared__ float red[8][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 256 + lane * 8;
-  const long long r0 = (long long)blockIdx.y * kRowsPerBlock;
-  const long long r1 = min(rows, r0 + kRowsPerBlock);
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -425,13 +428,19 @@ int d2r_bias_act_bwd(const void* dy, const void* y, int32_t dtype, int32_t act, 
   D2R_CHECK_ARG(cols % 8 == 0 && ld % 8 == 0, "bias_act_bwd: cols/ld must be multiples of 8");
   D2R_CHECK_ARG(act == D2R_ACT_NONE || y != nullptr, "bias_act_bwd: activation needs y");
   if (rows <= 0) return D2R_OK;
-  dim3 grid((cols + 255) / 256, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  // ~4 resident blocks per SM in ONE wave: a block streams a tall slab (>= 64 rows) so that its shared-memory
+  // reduction and its 256 atomics are amortised over many rows instead of paid once per 64 rows
+  const unsigned gx = (unsigned)((cols + 255) / 256);
+  const long long want_y = (4LL * num_sms() + gx - 1) / gx;
+  long long rpb = (rows + want_y - 1) / want_y;
+  rpb = (rpb + kRowsPerBlock - 1) / kRowsPerBlock * kRowsPerBlock;
+  dim3 grid(gx, (unsigned)((rows + rpb - 1) / rpb));
   if (act == D2R_ACT_NONE) {
-    D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T, false><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)y, act,
-                                                                                         (T*)dz, db, rows, cols, ld));
+    D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T, false><<<grid, kThreads, 0, st>>>(
+                                     (const T*)dy, (const T*)y, act, (T*)dz, db, rows, cols, ld, (int)rpb));
   } else {
-    D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T, true><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)y, act,
-                                                                                        (T*)dz, db, rows, cols, ld));
+    D2R_DISPATCH_DTYPE(dtype, T, bias_act_bwd_kernel<T, true><<<grid, kThreads, 0, st>>>(
+                                     (const T*)dy, (const T*)y, act, (T*)dz, db, rows, cols, ld, (int)rpb));
   }
   count_launch();
   return check_launch("bias_act_bwd_kernel");

@@ -300,28 +300,45 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   return check_launch("gemm_tc_kernel");
 }
 
-template <bool A_MN, bool B_MN>
+// How many clusters of `ctas` CTAs (1 CTA per SM) the device can hold at once: GPC boundaries make this less than
+// num_sms / ctas for the 4-CTA cluster, and a persistent grid must not be larger than what is co-resident.
+template <typename Kern>
+int max_clusters(Kern kern, int ctas, int smem_bytes) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(num_sms() / ctas * ctas), 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = num_sms() / ctas;
+  }
+  return n;
+}
+
+template <int PAIRS, bool A_MN, bool B_MN>
 int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                const TcParams& p, cudaStream_t stream) {
-  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto kern = gemm_tc2_kernel<PAIRS, A_MN, B_MN>;
+  static long long max_units = 0;
+  if (!max_units) {
     D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
-    attr_set = true;
+    max_units = PAIRS == 1 ? num_sms() / 2 : max_clusters(kern, 2 * PAIRS, Tc2Cfg::SMEM_BYTES);
   }
-  const long long max_pairs = num_sms() / 2;
-  const long long pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-  kern<<<(unsigned)(2 * pairs), kTcThreads, Tc2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+  const long long units = p.num_tiles < max_units ? p.num_tiles : max_units;
+  kern<<<(unsigned)(2 * PAIRS * units), kTcThreads, Tc2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
   count_launch();
   return check_launch("gemm_tc2_kernel");
 }
 
+template <int PAIRS>
 int launch_tc2_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                      const CUtensorMap& tmC2, const TcParams& p, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_tc2<false, false>(tmA, tmB, tmC, tmC2, p, stream);
-  if (!a_mn && b_mn) return launch_tc2<false, true>(tmA, tmB, tmC, tmC2, p, stream);
-  if (a_mn && !b_mn) return launch_tc2<true, false>(tmA, tmB, tmC, tmC2, p, stream);
-  return launch_tc2<true, true>(tmA, tmB, tmC, tmC2, p, stream);
+  if (!a_mn && !b_mn) return launch_tc2<PAIRS, false, false>(tmA, tmB, tmC, tmC2, p, stream);
+  if (!a_mn && b_mn) return launch_tc2<PAIRS, false, true>(tmA, tmB, tmC, tmC2, p, stream);
+  if (a_mn && !b_mn) return launch_tc2<PAIRS, true, false>(tmA, tmB, tmC, tmC2, p, stream);
+  return launch_tc2<PAIRS, true, true>(tmA, tmB, tmC, tmC2, p, stream);
 }
 
 template <int BN>
@@ -358,8 +375,10 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
 
   int bn = a.tile_n;
   bool pair = false;                       // CTA-pair kernel: 256 x 256 tiles, tcgen05.mma.cta_group::2
-  if (bn == 512) {
+  bool quad = false;                       // two pairs per cluster, 512 x 256 tiles, B multicast across the pairs
+  if (bn == 512 || bn == 1024) {
     pair = true;
+    quad = bn == 1024;
     bn = 256;
   } else if (bn == 0) {
     bn = a.n <= 64 ? 64 : (a.n <= 128 ? 128 : 256);
@@ -372,7 +391,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   }
   D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 192 || bn == 256, "gemm: tile_n %d unsupported", bn);
   D2R_CHECK_ARG(!softmax_epi || (!pair && bn >= a.n), "gemm: the softmax epilogues need the whole row in one tile");
-  const int bm = pair ? 2 * BM : BM;
+  const int bm = quad ? 4 * BM : (pair ? 2 * BM : BM);
 
   TcParams p;
   p.m = a.m; p.n = a.n; p.k = a.k;
@@ -431,7 +450,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   if (!a.a_mn_major) rc = encode_operand(&tmA, a.a, a.k, a.m, a_bi, a_bo, a.lda, a.a_si, a.a_so, BM);
   else               rc = encode_operand(&tmA, a.a, a.m, a.k, a_bi, a_bo, a.lda, a.a_si, a.a_so, BK);
   if (rc) return rc;
-  if (!a.b_mn_major) rc = encode_operand(&tmB, a.b, a.k, a.n, b_bi, b_bo, a.ldb, a.b_si, a.b_so, pair ? 128 : bn);
+  if (!a.b_mn_major) rc = encode_operand(&tmB, a.b, a.k, a.n, b_bi, b_bo, a.ldb, a.b_si, a.b_so, quad ? 64 : (pair ? 128 : bn));
   else               rc = encode_operand(&tmB, a.b, a.n, a.k, b_bi, b_bo, a.ldb, a.b_si, a.b_so, BK);
   if (rc) return rc;
 
@@ -457,7 +476,8 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
     }
   }
   const bool amn = a.a_mn_major != 0, bmn = a.b_mn_major != 0;
-  if (pair) return launch_tc2_major(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
+  if (quad) return launch_tc2_major<2>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
+  if (pair) return launch_tc2_major<1>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 64) return launch_tc_major<64>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 128) return launch_tc_major<128>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 192) return launch_tc_major<192>(amn, bmn, tmA, tmB, tmC, tmC2, p, stream);

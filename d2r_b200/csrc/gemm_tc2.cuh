@@ -11,6 +11,11 @@
 //   empty[s]       both CTAs, arrived by tcgen05.commit.cta_group::2 ... multicast (mask 0b11)
 //   tmem_full[a]   both CTAs, multicast commit after the last k-block of a tile
 //   tmem_empty[a]  leader only, count 16: 8 local epilogue warps + 8 remote arrives (mapa) from the peer
+//
+// PAIRS == 2 ("quad"): a cluster of two pairs stacked along M works on a 512 x 256 tile.  Both pairs need the same
+// B tile, so each CTA fetches only a 64-row quarter of its B half and TMA-multicasts it to its counterpart in the
+// other pair: the L2->SM fill per CTA and k-block drops again, 32 KB -> 24 KB.  A stage may then only be refilled
+// when BOTH pairs have consumed it: empty[s] counts one multicast commit per pair, sent to all four CTAs.
 #pragma once
 
 struct Tc2Cfg {
@@ -26,8 +31,8 @@ struct Tc2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+template <int PAIRS, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(kTcThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
   using Cfg = Tc2Cfg;
@@ -45,9 +50,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();          // 0 = leader, 1 = peer
-  const long long pair = blockIdx.x >> 1;
-  const long long npairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                  // inside the pair: 0 = leader (issues the MMAs), 1 = peer
+  const uint32_t pr = crank >> 1;                   // pair index inside the cluster (PAIRS == 2: stacked along M)
+  const long long pair = blockIdx.x / (2 * PAIRS);  // cluster index: one BM*2*PAIRS x 256 tile at a time
+  const long long npairs = gridDim.x / (2 * PAIRS);
+  constexpr uint16_t kAllCtas = PAIRS == 2 ? 0xF : 0x3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -58,7 +66,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIRS);              // one multicast commit per pair of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -83,7 +91,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       for (long long t = pair; t < p.num_tiles; t += npairs) {
         const TileCoord tc = decode_tile(p, t, BN);
-        const int m0 = tc.m0 + static_cast<int>(rank) * BM;
+        const int m0 = tc.m0 + static_cast<int>(pr) * 2 * BM + static_cast<int>(rank) * BM;
         const int nh = tc.n0 + static_cast<int>(rank) * Cfg::HALF_N;
         const int azi = p.a_bcast_i ? 0 : tc.zi, azo = p.a_bcast_o ? 0 : tc.zo;
         const int bzi = p.b_bcast_i ? 0 : tc.zi, bzo = p.b_bcast_o ? 0 : tc.zo;
@@ -101,7 +109,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int i = 0; i < BM / 64; ++i)
               tma_load_4d_2sm(sa + i * ATOM_BYTES, &tmA, &full_bar[stage], m0 + 64 * i, kb * BK, azi, azo);
           }
-          if constexpr (!B_MN) {
+          if constexpr (PAIRS == 2) {
+            // both pairs of the cluster multiply by the same B tile: this CTA fetches one 64-row quarter of its
+            // half and multicasts it to the CTA of the same parity in the other pair (and to itself)
+            const uint16_t mc = static_cast<uint16_t>(0x5u << rank);
+            const int nq = nh + 64 * static_cast<int>(pr);
+            uint8_t* sq = sb + pr * ATOM_BYTES;         // 64 rows x 128 B (K-major) or one 64x64 atom (MN-major)
+            if constexpr (!B_MN) tma_load_4d_2sm_mc(sq, &tmB, &full_bar[stage], mc, kb * BK, nq, bzi, bzo);
+            else                 tma_load_4d_2sm_mc(sq, &tmB, &full_bar[stage], mc, nq, kb * BK, bzi, bzo);
+          } else if constexpr (!B_MN) {
             tma_load_4d_2sm(sb, &tmB, &full_bar[stage], kb * BK, nh, bzi, bzo);
           } else {
 #pragma unroll
@@ -120,6 +136,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------- MMA issuer (leader CTA only)
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint16_t my_pair = static_cast<uint16_t>(0x3u << (2 * pr));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -142,13 +159,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                      : make_smem_desc_sw128(sb + k * 32, 16, 1024);
             umma_bf16_2sm(d_tmem, da, db, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_2sm(&empty_bar[stage]);          // frees the slot in BOTH CTAs
+          umma_commit_2sm(&empty_bar[stage], kAllCtas); // frees the slot in every CTA that (multi)casts into it
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[acc]);               // accumulator complete -> both epilogues
+        umma_commit_2sm(&tmem_full[acc], my_pair);      // accumulator complete -> both epilogues of this pair
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -160,7 +177,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* sb = sbias + (warp - 2) * BN;
     const int half = (warp - 2) >> 2;
     uint8_t* stg = store_stage + (warp - 2) * 2048;
-    const TileWalk walk{pair, npairs, static_cast<int>(rank) * BM, rank == 0 ? -1 : 0};
+    const TileWalk walk{pair, npairs, static_cast<int>(pr) * 2 * BM + static_cast<int>(rank) * BM,
+                        rank == 0 ? -1 : static_cast<int>(2 * pr)};
     using bf16 = __nv_bfloat16;
     switch (p.variant) {
       case EV_F32:        epilogue_loop<BN, float, NoRes, 0>(p, &tmC, &tmC2, tmem_base, tmem_full, tmem_empty, sb, stg, q, half, lane, walk); break;

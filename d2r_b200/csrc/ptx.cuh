@@ -199,6 +199,18 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const void* tmap
         "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Same, multicast: the box lands at the same shared-memory offset of every CTA in `cta_mask` (bit i = CTA rank i of
+// the cluster) and each destination pair's LEADER barrier receives the bytes delivered to its CTAs.
+__device__ __forceinline__ void tma_load_4d_2sm_mc(void* smem_dst, const void* tmap, uint64_t* bar, uint16_t cta_mask,
+                                                   int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask),
+        "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "r"(ncols)
@@ -222,8 +234,7 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
       : "memory");
 }
 // arrive (once the leader's previously issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-  const uint16_t mask = 3;
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),

@@ -74,7 +74,7 @@ typedef struct d2r_gemm_args {
   int32_t accumulate;  /* 1: C += result (fp32 C only, atomic) */
   int32_t split_k;     /* >1: split the k range over CTAs, fp32 C, atomic accumulation */
   float alpha;
-  int32_t tile_n;      /* 0 = auto; 64/128/256 forces the tensor-core N tile (tuning knob) */
+  int32_t tile_n;      /* 0 = auto; 64/128/192/256 force the tensor-core N tile, 512 the CTA-pair and 1024 the 4-CTA cluster kernel (tuning knob) */
   int32_t act_cols;    /* >0: the activation applies to output columns < act_cols only */
   int32_t reserved0;
   const void* a;

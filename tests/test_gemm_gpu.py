@@ -54,6 +54,15 @@ def test_tc_cta_pair(a_mn, b_mn, m, n, k):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("m,n,k", [(1024, 512, 192), (300, 333, 72), (1000, 768, 768), (4096, 768, 1536)])
+def test_tc_cta_quad(a_mn, b_mn, m, n, k):
+    """tile_n=1024 forces the 4-CTA cluster kernel: two cta_group::2 pairs on a 512x256 tile, the B tile TMA-
+    multicast across the pairs; ragged shapes leave whole CTAs of a cluster without rows."""
+    err, scale = _run(torch.bfloat16, m, n, k, a_mn, b_mn, 1024, batch=2)
+    assert err <= 2e-3 * scale + 1e-3, (err, scale)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", MAJORS)
 @pytest.mark.parametrize("m,n,k", [(200, 50, 72), (128, 48, 128), (130, 197, 768), (77, 300, 40)])
 def test_tc_ragged(a_mn, b_mn, m, n, k):
     err, scale = _run(torch.bfloat16, m, n, k, a_mn, b_mn, batch=3)

@@ -27,6 +27,14 @@ CASES = {
     "wgrad_tt": (768, 768, 32768, True, True, dict(out="f32", split_k=16)),
     "fwd_wide": (32768, 4608, 768, False, False, dict(bias=True, out="bf16")),
     "fwd_longk": (32768, 768, 4608, False, False, dict(out="bf16")),
+    "fwd_nt_quad": (32768, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=1024)),
+    "fwd_nt_pair": (32768, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=512)),
+    "dgrad_quad": (32768, 768, 768, False, True, dict(out="bf16", tile_n=1024)),
+    "img_nt_quad": (12800, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=1024)),
+    "img_nt_pair": (12800, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=512)),
+    "wgrad_quad": (768, 768, 32768, True, True, dict(out="f32", split_k=16, tile_n=1024)),
+    "fwd_wide_quad": (32768, 4608, 768, False, False, dict(bias=True, out="bf16", tile_n=1024)),
+    "fwd_longk_quad": (32768, 768, 4608, False, False, dict(out="bf16", tile_n=1024)),
     "small_tc": (256, 768, 768, False, False, dict(bias=True, out="f32")),
     "small_tc_bn128": (256, 768, 768, False, False, dict(bias=True, out="f32", tile_n=128)),
     "small_tc_bn64": (256, 768, 768, False, False, dict(bias=True, out="f32", tile_n=64)),
