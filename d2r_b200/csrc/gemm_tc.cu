@@ -37,7 +37,8 @@ struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;   // power of two; accumulators at 0 and BN
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BIAS_BYTES = 8 * BN * 4;   // one private bias slice per epilogue warp
+  static constexpr int BIAS_BYTES = 8 * (BN < 128 ? 128 : BN) * 4;   // one private bias slice per epilogue warp
+                                                                      // (>= 128 floats: softmax exchange slots)
   static constexpr int STORE_BYTES = 8 * 2048;    // one 32-row x 64-byte staging tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
@@ -57,7 +58,7 @@ struct TcParams {
   float alpha;
   int act, epilogue, c_dtype, r_dtype, atomic, act_cols, variant;
   int tma_store;   // 1: C (and c2) are written with TMA bulk tensor stores through a smem staging tile
-  int debug;   // D2R_TC_DEBUG env (bring-up only): 1 = skip epilogue stores, 2 = skip the epilogue body
+  int debug;   // D2R_TC_DEBUG env (bring-up only): 1 = skip epilogue stores, 2 = skip the epilogue body, 4 = no TMA stores
 };
 
 struct TileCoord {
@@ -210,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------- epilogue (4 warps)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    float* sb = sbias + (warp - 2) * BN;
+    float* sb = sbias + (warp - 2) * (BN < 128 ? 128 : BN);
     const int half = (warp - 2) >> 2;
     uint8_t* stg = store_stage + (warp - 2) * 2048;
     const TileWalk walk{static_cast<long long>(blockIdx.x), static_cast<long long>(gridDim.x), 0, -1};
@@ -464,7 +465,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
     const bool ok = (reinterpret_cast<uintptr_t>(a.c) & 15) == 0 && a.ldc % q == 0 &&
                     (bi == 1 || (a.c_si % q == 0 && a.c_si != 0)) && (bo == 1 || (a.c_so % q == 0 && a.c_so != 0)) &&
                     (a.epilogue != D2R_EPI_SQDIFF || (reinterpret_cast<uintptr_t>(a.c2) & 15) == 0);
-    p.tma_store = ok ? 1 : 0;
+    p.tma_store = (ok && !(p.debug & 4)) ? 1 : 0;   // debug bit 4: force per-thread global stores
     if (ok) {
       rc = encode_map(&tmC, a.c, es, a.n, a.m, bi, bo, a.ldc, a.c_si, a.c_so, 64 / es, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;

@@ -174,7 +174,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
     const int q = warp & 3;
-    float* sb = sbias + (warp - 2) * BN;
+    float* sb = sbias + (warp - 2) * (BN < 128 ? 128 : BN);
     const int half = (warp - 2) >> 2;
     uint8_t* stg = store_stage + (warp - 2) * 2048;
     const TileWalk walk{pair, npairs, static_cast<int>(pr) * 2 * BM + static_cast<int>(rank) * BM,

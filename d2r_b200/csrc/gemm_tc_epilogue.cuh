@@ -14,6 +14,16 @@
 
 struct NoRes {};
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// barrier of the two epilogue warps that share TMEM lane quarter q (named barriers 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int q) {
+  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+}
+
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -288,9 +298,101 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     const bool fast = (tc.n0 + BN <= p.n) && __all_sync(0xffffffffu, r_ok && row_ok);
     if constexpr (MODE == 3 || MODE == 4) {
       // ---- row softmax fused into the score GEMM (MODE 3) / its backward fused into the dP GEMM (MODE 4).
-      // The whole key dimension is one N tile (n <= BN), so a thread's TMEM lane holds its complete row: the
-      // row statistics need no cross-thread traffic at all, and S / dP never touch HBM.  Both warps of a pair
-      // compute the statistics of the full row (cheap TMEM re-reads) and then write their own half.
+      // The whole key dimension is one N tile (n <= BN), so the two warps that share a TMEM lane quarter hold a
+      // complete row between them: S / dP never touch HBM.
+      const float sc = p.alpha * 1.4426950408889634f;       // exp(alpha x) = 2^(alpha log2(e) x)
+      if (nchunks <= 4) {
+        // Each warp keeps ITS chunks (<= 2) in registers, reduces them, and swaps one partial result per row with
+        // its partner warp through shared memory (slot double-buffered by accumulator index: a warp cannot get
+        // two tiles ahead of its partner, the MMA of tile i+2 needs both warps' tmem_empty arrival for tile i).
+        float* xch = sbias_warp + acc * 64;
+        const float* xch_peer = xch + (half == 0 ? 4 : -4) * (BN < 128 ? 128 : BN);
+        if constexpr (MODE == 3) {
+          float e[64];
+          float ml = -INFINITY;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = cb + cc;
+            if (c < ce) {
+              uint32_t ra[32];
+              tmem_ld32(taddr + c * 32, ra);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = (c * 32 + i < ncols) ? sc * __uint_as_float(ra[i]) : -INFINITY;
+                e[cc * 32 + i] = x;
+                ml = fmaxf(ml, x);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[cc * 32 + i] = -INFINITY;
+            }
+          }
+          const float ms = ml == -INFINITY ? 0.f : ml;       // a warp without a valid column contributes 0
+          float sl = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            e[i] = ex2_ftz(e[i] - ms);
+            sl += e[i];
+          }
+          *reinterpret_cast<float2*>(xch + lane * 2) = make_float2(ml, sl);
+          pair_barrier(q);
+          const float2 pp = *reinterpret_cast<const float2*>(xch_peer + lane * 2);
+          const float mx = fmaxf(ml, pp.x);
+          const float mine = ex2_ftz(ml - mx);               // 2^(-inf) = 0
+          const float f = mine / (sl * mine + pp.y * ex2_ftz(pp.x - mx));
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = cb + cc;
+            if (c < ce) {
+              float v[32], d[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = e[cc * 32 + i] * f;
+              if (use_tma) tma_store_row32<CT>(tmC, stage, lane, v, c * 32, row0, tc.zi, tc.zo);
+              else if (row_ok) direct_store<CT, 0>(p, crow, c2row, c * 32, v, d);
+            }
+          }
+        } else {
+          float part = 0.f;
+#pragma unroll 1
+          for (int c = cb; c < ce; ++c) {            // pass 1: this warp's share of sum_j dP_j P_j
+            uint32_t ra[32];
+            tmem_ld32(taddr + c * 32, ra);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float pr[8];
+                ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) part = fmaf(p.alpha * __uint_as_float(ra[g * 8 + i]), pr[i], part);
+              }
+            }
+          }
+          xch[lane] = part;
+          pair_barrier(q);
+          const float tot = part + xch_peer[lane];
+#pragma unroll 1
+          for (int c = cb; c < ce; ++c) {            // pass 2: dS = P * (alpha dP - total)
+            uint32_t ra[32];
+            float v[32], d[32];
+            tmem_ld32(taddr + c * 32, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float pr[8];
+              if (row_ok) ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[g * 8 + i] = row_ok ? pr[i] * (p.alpha * __uint_as_float(ra[g * 8 + i]) - tot) : 0.f;
+            }
+            if (use_tma) tma_store_row32<CT>(tmC, stage, lane, v, c * 32, row0, tc.zi, tc.zo);
+            else if (row_ok) direct_store<CT, 0>(p, crow, c2row, c * 32, v, d);
+          }
+        }
+      } else {
+      // wide rows (128 < n <= 256): both warps compute the statistics of the full row (TMEM re-reads), then each
+      // writes its own half
       float stat0 = MODE == 3 ? -INFINITY : 0.f, stat1 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {          // pass 1: row max (fwd) / sum dP*P (bwd)
@@ -300,7 +402,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         if constexpr (MODE == 3) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < ncols) stat0 = fmaxf(stat0, p.alpha * __uint_as_float(ra[i]));
+            if (c * 32 + i < ncols) stat0 = fmaxf(stat0, sc * __uint_as_float(ra[i]));
         } else if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -319,7 +421,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < ncols) stat1 += __expf(p.alpha * __uint_as_float(ra[i]) - stat0);
+            if (c * 32 + i < ncols) stat1 += ex2_ftz(sc * __uint_as_float(ra[i]) - stat0);
         }
         stat1 = 1.f / stat1;
       }
@@ -332,7 +434,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         if constexpr (MODE == 3) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            v[i] = (c * 32 + i < ncols) ? __expf(p.alpha * __uint_as_float(ra[i]) - stat0) * stat1 : 0.f;
+            v[i] = (c * 32 + i < ncols) ? ex2_ftz(sc * __uint_as_float(ra[i]) - stat0) * stat1 : 0.f;
         } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -345,6 +447,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         }
         if (use_tma) tma_store_row32<CT>(tmC, stage, lane, v, c * 32, row0, tc.zi, tc.zo);
         else if (row_ok) direct_store<CT, 0>(p, crow, c2row, c * 32, v, d);
+      }
       }
     } else {
 #pragma unroll 1
