@@ -30,13 +30,19 @@ constexpr int kTcThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ATOM_BYTES = 64 * BK * 2;   // one [64 x 64] bf16 swizzle tile = 8 KB
 
+// Accumulator buffers in TMEM (512 fp32 columns per SM).  Wide tiles are double-buffered; the narrow tiles serve the
+// small-K batched products of the attention blocks, where a tile's main loop is one or two k-blocks and the tile
+// rate is set by the MMA -> epilogue -> MMA barrier round trip: more buffers keep more tiles in flight.
+constexpr int num_acc(int bn) { return bn >= 192 ? 2 : (bn == 128 ? 4 : 8); }
+
 template <int BN>
 struct TcCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
-  static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;   // power of two; accumulators at 0 and BN
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int NACC = num_acc(BN);
+  static constexpr int TMEM_COLS = 512;            // accumulator a at column a * BN
+  static constexpr int BAR_BYTES = 512;
   static constexpr int BIAS_BYTES = 8 * (BN < 128 ? 128 : BN) * 4;   // one private bias slice per epilogue warp
                                                                       // (>= 128 floats: softmax exchange slots)
   static constexpr int STORE_BYTES = 8 * 2048;    // one 32-row x 64-byte staging tile per epilogue warp
@@ -67,12 +73,15 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long t, int bn) {
   TileCoord tc;
-  int nb = static_cast<int>(t % p.n_tiles);
-  t /= p.n_tiles;
-  int ks = static_cast<int>(t % p.split_k);
-  t /= p.split_k;
-  int mb = static_cast<int>(t % p.m_tiles);
-  int z = static_cast<int>(t / p.m_tiles);
+  // 32-bit arithmetic (the host rejects launches with >= 2^31 tiles): a 64-bit divide is ~100 instructions, and
+  // the three role warps each decode every tile
+  unsigned u = static_cast<unsigned>(t);
+  const int nb = static_cast<int>(u % static_cast<unsigned>(p.n_tiles));
+  u /= static_cast<unsigned>(p.n_tiles);
+  const int ks = static_cast<int>(u % static_cast<unsigned>(p.split_k));
+  u /= static_cast<unsigned>(p.split_k);
+  const int mb = static_cast<int>(u % static_cast<unsigned>(p.m_tiles));
+  const int z = static_cast<int>(u / static_cast<unsigned>(p.m_tiles));
   tc.m0 = mb * p.bm;
   tc.n0 = nb * bn;
   tc.z = z;
@@ -98,8 +107,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + Cfg::NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::NACC);
   float* sbias = reinterpret_cast<float*>(store_stage + Cfg::STORE_BYTES + Cfg::BAR_BYTES);   // [8][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -116,7 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < Cfg::NACC; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);
     }
@@ -203,8 +212,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == Cfg::NACC) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
     __syncwarp();
@@ -405,6 +416,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   p.kb_per_split = (p.k_blocks + split_k - 1) / split_k;
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   p.num_tiles = 1LL * p.m_tiles * p.n_tiles * p.split_k * a.batch;
+  D2R_CHECK_ARG(p.num_tiles < (1LL << 31), "gemm: too many tiles");
   const bool atomic = a.accumulate || p.split_k > 1;
   D2R_CHECK_ARG(!atomic || a.c_dtype == D2R_F32, "gemm: accumulate/split_k need an fp32 C");
   D2R_CHECK_ARG(!atomic || (a.epilogue == D2R_EPI_STD && a.act == D2R_ACT_NONE && !a.residual),

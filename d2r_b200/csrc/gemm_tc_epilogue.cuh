@@ -303,9 +303,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       const float sc = p.alpha * 1.4426950408889634f;       // exp(alpha x) = 2^(alpha log2(e) x)
       if (nchunks <= 4) {
         // Each warp keeps ITS chunks (<= 2) in registers, reduces them, and swaps one partial result per row with
-        // its partner warp through shared memory (slot double-buffered by accumulator index: a warp cannot get
-        // two tiles ahead of its partner, the MMA of tile i+2 needs both warps' tmem_empty arrival for tile i).
-        float* xch = sbias_warp + acc * 64;
+        // its partner warp through shared memory (two slots, alternating per tile: the pair barrier of tile i+1
+        // cannot complete before the partner has read the slot of tile i).
+        float* xch = sbias_warp + (acc & 1) * 64;
         const float* xch_peer = xch + (half == 0 ? 4 : -4) * (BN < 128 ? 128 : BN);
         if constexpr (MODE == 3) {
           float e[64];
@@ -484,8 +484,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       if (w.remote_cta < 0) mbar_arrive(&tmem_empty[acc]);
       else mbar_arrive_cluster(&tmem_empty[acc], static_cast<uint32_t>(w.remote_cta));
     }
-    acc ^= 1;
-    if (acc == 0) acc_phase ^= 1;
+    if (++acc == num_acc(BN)) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
   }
   if (lane == 0) bulk_wait_all();          // all bulk stores of this warp are complete before the CTA exits
   __syncwarp();
