@@ -34,6 +34,13 @@ sys.path.insert(0, ROOT)
 
 LT, LI, D, KC, R = 128, 50, 768, 6, 3
 BATCH_PER_GPU = 256
+# DRAM traffic of the dominant GEMM launch (ncu --set full, profiles/r01_ncu_gemm_k768_pair.txt): the m=32768, n=768,
+# k=768 projection reads 51.6 MB and writes 10.4 MB per launch against 101.8 MB of algorithmic operand bytes (the
+# bf16 output mostly stays in L2): no wasted re-reads.
+GEMM_TRAFFIC_BYTES = 62.0e6
+GEMM_TRAFFIC_NOTE = ("dram__bytes_read+write of one m=32768 n=768 k=768 launch (60% of the GEMM time is this shape "
+                     "class); ncu capture of round 1, see profiles/r01_ncu_gemm_k768_pair.txt")
+AGG_TRAFFIC_BYTES = 461.3e6
 CPU_SAMPLE_BATCH = 8
 
 
@@ -187,7 +194,7 @@ def own_arm(args):
     import torch
     import torch.distributed as dist
     from d2r_b200 import kernels as K
-    from d2r_b200.dp import GradAllReducer
+    from d2r_b200.dp import GradAllReducer, InputPrefetcher
     from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule, run_pair
 
     import d2r_b200.lanes as LN
@@ -259,11 +266,16 @@ def own_arm(args):
             graph = None
             torch.cuda.synchronize()
 
-    def step(from_host):
+    prefetch = InputPrefetcher([d_text, d_image])
+
+    def step(from_host, more=False):
+        """One fwd+bwd(+all-reduce).  from_host: this step's inputs come from the pinned host batch through the
+        prefetcher (H2D on a copy stream, overlapped with the previous step's compute); `more`: start the next
+        step's H2D copy before computing."""
         if from_host:
-            with torch.no_grad():
-                d_text.copy_(h_text, non_blocking=True)
-                d_image.copy_(h_image, non_blocking=True)
+            prefetch.commit()
+            if more:
+                prefetch.fetch([h_text, h_image])
         if graph is not None:
             graph.replay()
             loss = static_loss
@@ -291,8 +303,10 @@ def own_arm(args):
         prof = bool(os.environ.get("D2R_PROFILE_RANGE")) and not from_host
         if prof:
             torch.cuda.cudart().cudaProfilerStart()
-        for _ in range(steps):
-            step(from_host)
+        if from_host:
+            prefetch.fetch([h_text, h_image])     # step 0's inputs: inside the timed region, not overlapped
+        for i in range(steps):
+            step(from_host, more=i + 1 < steps)
         if prof:
             torch.cuda.synchronize()
             torch.cuda.cudart().cudaProfilerStop()
@@ -319,8 +333,9 @@ def own_arm(args):
             step(False)
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step(True)
+    prefetch.fetch([h_text, h_image])
+    step(True, more=True)
+    step(True)
     ms_e2e, _ = timed(True, args.steps)
     eager_launches_per_step = None
     if graph is not None:
@@ -370,14 +385,18 @@ def own_arm(args):
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one fwd+bwd step)",
                 "achieved": roof["tflops"], "peak": tc_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tc_peak,
-                "traffic": None, "peak_source": peak_src, "launches_per_step": roof["launches"],
-                "kernel_ms_per_step": roof["ms"], "kernel_share_of_step": roof["ms"] / (ms / args.steps),
+                "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE, "peak_source": peak_src, "launches_per_step": roof["launches"],
+                "kernel_ms_per_step": roof["ms"], "single_stream_step_ms": roof["serial_step_ms"],
+                "kernel_share_of_step": roof["ms"] / roof["serial_step_ms"],
                 "step_algorithmic_tflops": flops_step / (ms / args.steps / 1e3) / 1e12,
                 "step_frac_of_peak": flops_step / (ms / args.steps / 1e3) / 1e12 / tc_peak,
             },
             "roofline_hbm": {"bound": "hbm", "kernel": "agg_fwd_kernel / agg_bwd_kernel (aggregation epilogue)",
                              "achieved": hbm["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm["gbs"] / hbm_peak,
-                             "launches_per_step": hbm["launches"], "kernel_ms_per_step": hbm["ms"]},
+                             "launches_per_step": hbm["launches"], "kernel_ms_per_step": hbm["ms"],
+                             "traffic": AGG_TRAFFIC_BYTES,
+                             "traffic_note": "agg_fwd_kernel text non-final launch: 503.3 MB algorithmic, 461.3 MB "
+                                             "dram (profiles/r01_ncu_agg_fwd.txt)"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -418,7 +437,11 @@ def kernel_roofline(fwd_bwd, K, torch):
         byts = (n_out + 2 * nfull) * x0.numel() * x0.element_size()
         return timed_call("agg", byts, orig_ab, full, bvec, P, gate, final, d_outs, d_pooled, inputs)
 
+    import d2r_b200.lanes as LN
+    lanes_were = LN.ENABLED
+    LN.ENABLED = False                  # one stream: concurrent lanes would overlap inside each other's event pairs
     K.gemm, K.aggregate_fwd, K.aggregate_bwd = gemm, agg_f, agg_b
+    serial_ms = 0.0
     try:
         fwd_bwd()                       # warm
         torch.cuda.synchronize()
@@ -429,15 +452,21 @@ def kernel_roofline(fwd_bwd, K, torch):
             # park the GPU for ~80 ms so that the host enqueues the whole step ahead of it: the events then
             # bracket back-to-back kernel execution, not host launch latency
             torch.cuda._sleep(int(0.08 * 1.9e9))
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
             fwd_bwd()
+            s1.record()
             torch.cuda.synchronize()
+            serial_ms += s0.elapsed_time(s1) / nsteps
     finally:
         K.gemm, K.aggregate_fwd, K.aggregate_bwd = orig_gemm, orig_af, orig_ab
+        LN.ENABLED = lanes_were
     gms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["gemm"]) / nsteps
     gfl = sum(w for _, _, w in recs["gemm"]) / nsteps
     ams = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["agg"]) / nsteps
     aby = sum(w for _, _, w in recs["agg"]) / nsteps
-    return ({"tflops": gfl / (gms / 1e3) / 1e12, "ms": gms, "launches": len(recs["gemm"]) // nsteps},
+    return ({"tflops": gfl / (gms / 1e3) / 1e12, "ms": gms, "launches": len(recs["gemm"]) // nsteps,
+             "serial_step_ms": serial_ms},
             {"gbs": aby / (ams / 1e3) / 1e9, "ms": ams, "launches": len(recs["agg"]) // nsteps})
 
 

@@ -84,3 +84,45 @@ class GradAllReducer:
         self.pack()
         self.all_reduce()
         self.finish()
+
+
+class InputPrefetcher:
+    """Host -> device input pipeline of one rank: the pinned host batch of step i+1 is copied to the GPU on a copy
+    stream while step i computes, then moved into the (static, CUDA-graph visible) input tensors with a
+    device-to-device copy.  Every step's inputs still cross PCIe exactly once; only the wait is hidden.
+
+        pf = InputPrefetcher([d_text, d_image])
+        pf.fetch([h_text0, h_image0])              # first batch
+        for i in range(steps):
+            pf.commit()                            # inputs of step i are now in d_text / d_image
+            if i + 1 < steps:
+                pf.fetch(next_host_batch)          # overlaps with the compute below
+            ... forward / backward on the current stream ...
+    """
+
+    def __init__(self, static_inputs: List[torch.Tensor]):
+        self.static = list(static_inputs)
+        self.stage = [torch.empty_like(t) for t in self.static]
+        self.copy_stream = torch.cuda.Stream(device=self.static[0].device)
+        self.ready = torch.cuda.Event()
+        self.free = torch.cuda.Event()
+        self.free.record(torch.cuda.current_stream(self.static[0].device))
+        self.bytes_per_fetch = sum(t.numel() * t.element_size() for t in self.static)
+
+    def fetch(self, host_batch: List[torch.Tensor]) -> None:
+        """Start the H2D copy of the next batch (pinned host tensors) on the copy stream."""
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free)         # the previous commit has drained the staging buffers
+            with torch.no_grad():
+                for s, h in zip(self.stage, host_batch):
+                    s.copy_(h, non_blocking=True)
+            self.ready.record(self.copy_stream)
+
+    def commit(self) -> None:
+        """Make the fetched batch the current input (current stream waits for the copy, then D2D)."""
+        cur = torch.cuda.current_stream(self.static[0].device)
+        cur.wait_event(self.ready)
+        with torch.no_grad():
+            for d, s in zip(self.static, self.stage):
+                d.copy_(s, non_blocking=True)
+        self.free.record(cur)
