@@ -101,12 +101,23 @@ class Env:
 
 # ----------------------------------------------------------------------------- linear helpers
 def _split_k(m_out: int, n_out: int, k: int, tc: bool) -> int:
+    """Split-K factor of a weight-gradient GEMM (k = B*L rows).  Tensor-core path: the long-k products run on
+    CTA pairs (256x256 tiles, 74 pairs); pick the factor that minimises waves x (k-blocks per split + the cost
+    of one fp32 reduce-add epilogue, ~6 k-blocks)."""
     if tc:
-        tiles = ((m_out + 127) // 128) * ((n_out + 255) // 256)
+        pair = k >= 1536
+        tiles = ((m_out + 255) // 256 if pair else (m_out + 127) // 128) * ((n_out + 255) // 256)
+        workers = 74 if pair else 148
         kb = (k + 63) // 64
-    else:
-        tiles = ((m_out + 63) // 64) * ((n_out + 63) // 64)
-        kb = (k + 15) // 16
+        best, best_cost = 1, None
+        for sk in range(1, min(kb, 64) + 1):
+            waves = (tiles * sk + workers - 1) // workers
+            cost = waves * ((kb + sk - 1) // sk + 6)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = sk, cost
+        return best
+    tiles = ((m_out + 63) // 64) * ((n_out + 63) // 64)
+    kb = (k + 15) // 16
     want = max(1, (2 * 148) // tiles)      # <= 2 full waves of 148 SMs
     return max(1, min(want, kb, 64))
 

@@ -25,6 +25,11 @@ CASES = {
     "fwd_nt_res": (32768, 768, 768, False, False, dict(bias=True, out="bf16", residual=True, act=L.ACT_RELU)),
     "dgrad_nn": (32768, 768, 768, False, True, dict(out="bf16")),
     "wgrad_tt": (768, 768, 32768, True, True, dict(out="f32", split_k=16)),
+    "wgrad_sk8": (768, 768, 32768, True, True, dict(out="f32", split_k=8)),
+    "wgrad_img_sk16": (768, 768, 12800, True, True, dict(out="f32", split_k=16)),
+    "wgrad_img_sk8": (768, 768, 12800, True, True, dict(out="f32", split_k=8)),
+    "wgrad_wide_sk2": (4608, 768, 32768, True, True, dict(out="f32", split_k=2)),
+    "wgrad_wide_sk4": (4608, 768, 32768, True, True, dict(out="f32", split_k=4)),
     "fwd_wide": (32768, 4608, 768, False, False, dict(bias=True, out="bf16")),
     "fwd_longk": (32768, 768, 4608, False, False, dict(out="bf16")),
     "fwd_nt_quad": (32768, 768, 768, False, False, dict(bias=True, out="bf16", tile_n=1024)),
