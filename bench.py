@@ -133,7 +133,7 @@ def reference_arm(args):
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -206,7 +206,6 @@ def own_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = BATCH_PER_GPU
 
@@ -399,7 +398,7 @@ def own_arm(args):
                                              "dram (profiles/r01_ncu_agg_fwd.txt)"},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -470,7 +469,27 @@ def kernel_roofline(fwd_bwd, K, torch):
             {"gbs": aby / (ams / 1e3) / 1e9, "ms": ams, "launches": len(recs["agg"]) // nsteps})
 
 
+_JSON_OUT = None
+
+
+def reserve_stdout():
+    """Keep the process' stdout for the ONE JSON line: libraries (NCCL's version banner, ...) write to file
+    descriptor 1 directly, so fd 1 is pointed at stderr and the original stdout is kept aside for emit()."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -485,8 +504,7 @@ def main():
     args = ap.parse_args()
     if args.cpu_sample:
         r = run_cpu_reference(steps=4, warmup=1)
-        print(json.dumps({"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                          "sample": r["sample"]}))
+        emit({"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]})
         return 0
     if args.impl == "reference":
         return reference_arm(args)
