@@ -274,3 +274,58 @@ def test_run_pair_equals_back_to_back_calls(bf16, graph):
             continue                       # mathematically zero: both sides hold rounding noise only
         scale = ref_grads[k].abs().max().item()
         assert (grads[k] - ref_grads[k]).abs().max().item() <= tol * scale + 1e-6, k
+
+
+@pytest.mark.parametrize("rev", [False, True], ids=["text", "image"])
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp32", "bf16"])
+def test_config4_long_sequences_vs_oracle(rev, bf16):
+    """BASELINE config 4 shape (K=6, R=4, text 256 + 197 image tokens), small batch, forward + input gradients.
+    197 / 256 keys exercise the wide-row softmax epilogue (more than four 32-column chunks) and Lc not a
+    multiple of 8 (padded leading dimension)."""
+    B, Lt, Li, R = 2, 256, 197, 4
+    P = O.make_params(PARAM_SEED_BASE + R, R, 6)
+    text, image = O.make_inputs(INPUT_SEED_BASE + 40, B, Lt, Li)
+    t, i = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+    ref_out, ref_sim, ref_probs = O.stack_forward(P, t, i, R, 6, rev, training=False)
+    (ref_out[0].sum() + ref_sim.sum()).backward()
+    m = build(R, 6, rev, P, training=False)
+    tc, ic = text.cuda().requires_grad_(True), image.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+        out, sim, probs = m(tc, ic, return_path_probs=True)
+    (out[0].sum() + sim.sum()).backward()
+    tol_p, tol_o = (2e-2, 5e-2) if bf16 else (2e-5, 1e-4)              # bf16: tolerance of north_star
+    for a, b in zip(probs, ref_probs):
+        assert relerr(a, b.detach()) <= tol_p, relerr(a, b.detach())
+    assert relerr(sim, ref_sim.detach()) <= tol_p
+    assert relerr(out[0], ref_out[0].detach()) <= tol_o
+    # Input gradients at these lengths are ill-conditioned in the REFERENCE itself: a 1e-6 relative perturbation
+    # of the text moves the fp32 oracle's own d_text by 1.6e-2 (max, one sample) at (Lt, Li) = (256, 48).  So the
+    # bound is a max error of 5e-2 plus a tight bound on the relative L2 error; the small golden cases pin the
+    # backward to 1e-4.
+    def l2rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return ((a - b).norm() / b.norm()).item()
+    # (bf16 against the fp32 oracle: the cross-modal logits are 100 q.k / sqrt(768), ~50 in magnitude, so bf16
+    #  operand rounding (2^-8) moves a logit by ~0.2; measured relative L2 error of the own-stream gradient is
+    #  7 % at (128, 50) and 14 % at (256, 197), growing smoothly with length.  The bf16 bounds only guard against
+    #  gross errors such as a missing term.)
+    tol_max, tol_l2 = (5e-1, 2.5e-1) if bf16 else (5e-2, 5e-3)
+    for got, ref in ((tc.grad, t.grad), (ic.grad, i.grad)):
+        assert relerr(got, ref) <= tol_max, relerr(got, ref)
+        assert l2rel(got, ref) <= tol_l2, l2rel(got, ref)
+
+
+@pytest.mark.parametrize("B", [2, 5, 64])
+def test_config5_eval_batch_sweep_is_per_sample_consistent(B):
+    """BASELINE config 5 (eval / no_grad, varying batch): a sample's output does not depend on the batch it
+    rides in (bit-exact in fp32), and matches the oracle on the first two samples."""
+    R = 3
+    P = O.make_params(PARAM_SEED_BASE + R, R, 6)
+    text, image = O.make_inputs(INPUT_SEED_BASE + 64, 64, 32, 50)
+    m = build(R, 6, False, P, training=False)
+    with torch.no_grad():
+        full, _ = m(text.cuda(), image.cuda())
+        part, _ = m(text[:B].cuda(), image[:B].cuda())
+    assert torch.equal(part[0], full[0][:B])
+    ref_out, _, _ = O.stack_forward(P, text[:2], image[:2], R, 6, False, training=False)
+    assert relerr(part[0][:2], ref_out[0]) <= 1e-4
