@@ -225,7 +225,13 @@ def own_arm(args):
         d_text.copy_(h_text)
         d_image.copy_(h_image)
 
-    def fwd_bwd(serial=args.serial_branches):
+    # gradient all-reduce: layer-wise, launched from inside the backward (overlapped), or one collective per step
+    overlap = args.overlap_allreduce
+    if overlap:
+        reducer.install()
+
+    def fwd_bwd(serial=args.serial_branches, reduce=True):
+        reducer.active = overlap and reduce
         d_text.grad = None
         d_image.grad = None
         for m in (mt, mi):
@@ -240,6 +246,10 @@ def own_arm(args):
                 (o1, s1), (o2, s2) = run_pair(mt, mi, d_text, d_image)
         loss = o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()
         loss.backward()
+        if reducer.active:
+            reducer.wait()
+        elif reduce:
+            reducer.pack()
         return loss
 
     # --- optional CUDA graph of fwd+bwd (+ gradient packing) --------------------------------------
@@ -249,7 +259,6 @@ def own_arm(args):
     with torch.cuda.stream(side):
         for _ in range(2):
             loss = fwd_bwd()
-            reducer.pack()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     if use_graph:
@@ -257,7 +266,6 @@ def own_arm(args):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_loss = fwd_bwd()
-                reducer.pack()
             graph.replay()
             torch.cuda.synchronize()
         except Exception as e:   # report and continue eagerly
@@ -280,8 +288,8 @@ def own_arm(args):
             loss = static_loss
         else:
             loss = fwd_bwd()
-            reducer.pack()
-        reducer.all_reduce()
+        if not overlap:
+            reducer.all_reduce()
         if from_host:
             h_loss.copy_(loss.detach().float().reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -340,14 +348,14 @@ def own_arm(args):
     if graph is not None:
         # kernels launched from a replayed graph do not pass through the C ABI: count one eager step
         n0 = K.L.launch_count()
-        fwd_bwd()
+        fwd_bwd(reduce=False)
         torch.cuda.synchronize()
         eager_launches_per_step = K.L.launch_count() - n0
         launches = eager_launches_per_step * args.steps
 
     # --- per-kernel roofline pass (separate, eager, CUDA events around every C-ABI GEMM launch) -----
     # (branches back to back here: kernels of concurrent streams would overlap inside each other's event pairs)
-    roof, hbm = kernel_roofline(lambda: fwd_bwd(serial=True), K, torch) if rank == 0 else (None, None)
+    roof, hbm = kernel_roofline(lambda: fwd_bwd(serial=True, reduce=False), K, torch) if rank == 0 else (None, None)
 
     if rank == 0:
         peaks = {}
@@ -375,7 +383,9 @@ def own_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world) | {"cuda_graph": graph is not None,
                                                   "branch_streams": 1 if args.serial_branches else 2,
-                                                  "cell_lanes": LN.CELL_LANES},
+                                                  "cell_lanes": LN.CELL_LANES,
+                                                  "allreduce": "layer-wise, inside the backward" if overlap
+                                                  else "one per step"},
             "clocks": clocks,
             "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": (h_text.numel() + h_image.numel()) * 4, "d2h_bytes_per_step": 4,
@@ -497,6 +507,9 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--serial-branches", action="store_true",
                     help="call the two branch modules back to back instead of run_pair (two CUDA streams)")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="layer-wise gradient all-reduces launched from inside the backward (GradAllReducer.install) "
+                         "instead of one collective after it; measured equal at 2 GPUs in round 1, not the default")
     ap.add_argument("--cell-lanes", type=int, default=None,
                     help="CUDA streams per routing layer (default: d2r_b200.lanes.CELL_LANES; 1 = one stream)")
     ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")

@@ -38,11 +38,12 @@ def _stager_of(module: torch.nn.Module) -> S.Stager:
 
 def _fwd_one(spec, tensors):
     """Run one block's forward on the CURRENT stream -> (outs, record for the backward)."""
-    n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = spec
+    n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = spec[:10]
     inputs = tensors[:n_in]
     P: Dict[str, Tensor] = dict(zip(names, tensors[n_in:]))
     P.update(bufs)
     env = S.Env(P, cd, training, stager, heads)
+    env.layer_hook = spec[10]
     x_cd = [None if t is None else t.detach().to(cd).contiguous() for t in inputs]
     outs, state = fwd(env, x_cd)
     rec = dict(spec=spec, state=state, in_dtypes=[None if t is None else t.dtype for t in inputs],
@@ -52,7 +53,7 @@ def _fwd_one(spec, tensors):
 
 def _bwd_one(rec, grads) -> List[Optional[Tensor]]:
     """Run one block's backward on the CURRENT stream -> [input grads..., parameter grads...]."""
-    n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = rec["spec"]
+    n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = rec["spec"][:10]
     # parameters are only needed by name -> the forward's tensors are reachable through the state's env
     env: S.Env = rec["state"]["env"]
     env.G = {}
@@ -138,8 +139,9 @@ def _make_spec(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]], fwd:
         state["env"] = env
         return outs, state
 
+    # optional per-layer gradient callback (d2r_b200.dp.GradAllReducer.install): layer prefix, {name: grad}
     spec = (len(inputs), tuple(names), bufs, fwd_wrapped, bwd, cd, module.training, _stager_of(module), heads,
-            tuple(out_nondiff))
+            tuple(out_nondiff), module.__dict__.get("_d2r_layer_hook"))
     return spec, list(inputs) + params
 
 

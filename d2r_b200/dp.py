@@ -35,43 +35,88 @@ def shard_batch(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+LAYER_HOOK_ATTR = "_d2r_layer_hook"
+
+
+def _layer_of(name: str) -> str:
+    """'dynamic_itr_l1.0.imrc...' -> 'dynamic_itr_l1.0'; 'dynamic_itr_l2.glac...' -> 'dynamic_itr_l2'."""
+    parts = name.split(".")
+    return ".".join(parts[:2]) if parts[0] == "dynamic_itr_l1" else parts[0]
+
+
 class GradAllReducer:
-    """Flat-bucket mean all-reduce of the live parameter gradients of one or more modules."""
+    """Flat-bucket mean all-reduce of the live parameter gradients of one or more stack modules.
+
+    Two ways to drive it:
+      * ``step()`` (= ``pack(); all_reduce(); finish()``) after ``loss.backward()``: one collective per step;
+      * ``install()``: the stack's backward calls back after every routing layer (last layer first) with that
+        layer's finished gradients; they are copied into the layer's slice of the flat bucket and the slice's
+        all-reduce is launched at once (async, NCCL's stream), so it runs under the backward of the earlier
+        layers and of the other stack.  ``wait()`` joins them; the pattern is capturable in a CUDA graph.
+    The flat bucket is ordered by completion (module, layer in backward order), so both ways end in the same
+    state: ``p.grad`` views of one reduced buffer.
+    """
 
     def __init__(self, modules: Iterable[torch.nn.Module], group: Optional[dist.ProcessGroup] = None):
         self.group = group
+        self.modules = list(modules)
         self.params: List[torch.nn.Parameter] = []
         self.names: List[str] = []
-        for mi, m in enumerate(modules):
-            for n, p in m.named_parameters():
-                if p.requires_grad and is_live(n):
-                    self.params.append(p)
-                    self.names.append(f"{mi}.{n}")
+        self.slices = {}                      # (module index, layer prefix) -> (first param idx, end idx, off, numel)
+        for mi, m in enumerate(self.modules):
+            live = [(n, p) for n, p in m.named_parameters() if p.requires_grad and is_live(n)]
+            layers: List[str] = []
+            for n, _ in live:
+                if _layer_of(n) not in layers:
+                    layers.append(_layer_of(n))
+            for layer in reversed(layers):    # the backward finishes the last routing layer first
+                i0, off = len(self.params), sum(p.numel() for p in self.params)
+                for n, p in live:
+                    if _layer_of(n) == layer:
+                        self.params.append(p)
+                        self.names.append(f"{mi}.{n}")
+                self.slices[(mi, layer)] = (i0, len(self.params), off,
+                                            sum(p.numel() for p in self.params[i0:]))
         self.numel = sum(p.numel() for p in self.params)
         self.flat: Optional[torch.Tensor] = None
+        self._views: Optional[List[torch.Tensor]] = None
+        self._works: list = []
+        self._filled = 0
+        self.active = True                    # install()ed callbacks do nothing while this is False
 
+    # ------------------------------------------------------------------ shared
+    def _ensure_flat(self) -> None:
+        if self.flat is None:
+            p0 = self.params[0]
+            self.flat = torch.empty(self.numel, device=p0.device, dtype=torch.float32)
+            views, off = [], 0
+            for p in self.params:
+                views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._views = views
+
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _reduce(self, t: torch.Tensor, async_op: bool):
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG if t.is_cuda else dist.ReduceOp.SUM, group=self.group,
+                               async_op=async_op)
+
+    # ------------------------------------------------------------------ one collective per step
     def pack(self) -> torch.Tensor:
         """Copy every live gradient into the flat bucket (one fused copy); missing gradients are a bug."""
         missing = [n for n, p in zip(self.names, self.params) if p.grad is None]
         if missing:
             raise RuntimeError(f"GradAllReducer: live parameters without gradient: {missing[:3]} ...")
-        if self.flat is None:
-            p0 = self.params[0]
-            self.flat = torch.empty(self.numel, device=p0.device, dtype=torch.float32)
-        views, off = [], 0
-        for p in self.params:
-            views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        torch._foreach_copy_(views, [p.grad for p in self.params])
-        self._views = views
+        self._ensure_flat()
+        torch._foreach_copy_(self._views, [p.grad for p in self.params])
         return self.flat
 
     def all_reduce(self, async_op: bool = False):
         """Mean all-reduce of the packed bucket (call pack() first)."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+        if not self._distributed():
             return None
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM,
-                               group=self.group, async_op=async_op)
+        return self._reduce(self.flat, async_op)
 
     def finish(self) -> None:
         """Point p.grad at the reduced bucket (gloo has no AVG: divide here)."""
@@ -84,6 +129,45 @@ class GradAllReducer:
         self.pack()
         self.all_reduce()
         self.finish()
+
+    # ------------------------------------------------------------------ layer-wise, overlapped with the backward
+    def install(self) -> None:
+        """Register the per-layer callback on the modules (picked up by the stack's autograd node)."""
+        for mi, m in enumerate(self.modules):
+            m.__dict__[LAYER_HOOK_ATTR] = (lambda layer, grads, _mi=mi: self.on_layer(_mi, layer, grads))
+
+    def uninstall(self) -> None:
+        for m in self.modules:
+            m.__dict__.pop(LAYER_HOOK_ATTR, None)
+
+    def on_layer(self, mi: int, layer: str, grads) -> None:
+        """``grads``: name -> finished gradient for (at least) every live parameter of ``layer`` of module ``mi``.
+        Runs on the stream that computed them."""
+        if not self.active:
+            return
+        i0, i1, off, numel = self.slices[(mi, layer)]
+        self._ensure_flat()
+        prefix = f"{mi}."
+        src = []
+        for n in self.names[i0:i1]:
+            g = grads.get(n[len(prefix):])
+            if g is None:
+                raise RuntimeError(f"GradAllReducer: live parameter without gradient: {n}")
+            src.append(g)
+        torch._foreach_copy_(self._views[i0:i1], src)
+        self._filled += 1
+        if self._distributed():
+            self._works.append(self._reduce(self.flat[off:off + numel], async_op=True))
+
+    def wait(self) -> None:
+        """Join the layer collectives (the current stream waits; no host block for NCCL)."""
+        if self._filled != len(self.slices):
+            raise RuntimeError(f"GradAllReducer: {self._filled} of {len(self.slices)} layer buckets were filled")
+        for w in self._works:
+            w.wait()
+        self._works, self._filled = [], 0
+        if not self.flat.is_cuda and self._distributed():
+            self.flat.div_(dist.get_world_size(self.group))
 
 
 class InputPrefetcher:

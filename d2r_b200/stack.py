@@ -81,6 +81,7 @@ class Env:
         self.cd = cd
         self.training = training
         self.st = stager
+        self.layer_hook = None         # callable(layer prefix, {name: grad}) after each layer's backward
         self.heads = heads
         self.G: Dict[str, Tensor] = {}
 
@@ -697,6 +698,10 @@ def stack_backward(env: Env, state, d_out: Optional[Tensor], d_sim: Optional[Ten
         d_xs, d_pooled, dz = layer_backward(env, pres[li], st, d_cur, d_pooled_next, extra, dz, shared_input=li == 0)
         d_cur, d_pooled_next = d_xs, d_pooled
         states[li] = None
+        if env.layer_hook is not None:
+            # every parameter gradient of this routing layer is final: hand them over (data-parallel runs start
+            # the layer's all-reduce here, under the backward of the earlier layers)
+            env.layer_hook(pres[li], env.G)
     # layer 0: d_cur = [sum of the cell gradients]; add the routers' mean-pool gradient (broadcast over L)
     dx = d_cur[0]
     K.pool_mean_bwd_into(d_pooled_next[0], dx)

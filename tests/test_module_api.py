@@ -146,3 +146,76 @@ def test_dp_allreduce_gloo_world2():
         lin(x[lo:hi]).pow(2).mean().backward()
         gs.append(lin.weight.grad.clone())
     torch.testing.assert_close(res[0][1], (gs[0] + gs[1]) / 2)
+
+
+def _dp_layerwise_worker(rank, world, port, q):
+    """Layer-wise reducer driven the way stack_backward drives it: last routing layer first, one callback per
+    layer with that layer's finished gradients; compared with the one-collective path on the same gradients."""
+    import torch.distributed as dist
+    from d2r_b200.dp import GradAllReducer, LAYER_HOOK_ATTR
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(4, 4)
+
+    class TinyStack(torch.nn.Module):      # parameter names of a routed stack: l0, l1.<i>, l2 + dead ones
+        def __init__(self):
+            super().__init__()
+            self.dynamic_itr_l0 = Layer()
+            self.dynamic_itr_l1 = torch.nn.ModuleList([Layer(), Layer()])
+            self.dynamic_itr_l2 = Layer()
+            self.path_mapping = torch.nn.Linear(3, 2)
+
+    torch.manual_seed(1)
+    mods = [TinyStack(), TinyStack()]
+    g = torch.Generator().manual_seed(100 + rank)
+    grads = [{n: torch.randn(p.shape, generator=g) for n, p in m.named_parameters()} for m in mods]
+    red = GradAllReducer(mods)
+    assert [k for k in red.slices] == [(0, "dynamic_itr_l2"), (0, "dynamic_itr_l1.1"), (0, "dynamic_itr_l1.0"),
+                                       (0, "dynamic_itr_l0"), (1, "dynamic_itr_l2"), (1, "dynamic_itr_l1.1"),
+                                       (1, "dynamic_itr_l1.0"), (1, "dynamic_itr_l0")]
+    red.install()
+    for mi, m in enumerate(mods):
+        hook = m.__dict__[LAYER_HOOK_ATTR]
+        for layer in ("dynamic_itr_l2", "dynamic_itr_l1.1", "dynamic_itr_l1.0", "dynamic_itr_l0"):
+            hook(layer, grads[mi])
+    red.wait()
+    layerwise = red.flat.clone()
+    # reference: the one-collective path on the same per-rank gradients
+    for mi, m in enumerate(mods):
+        for n, p in m.named_parameters():
+            p.grad = grads[mi][n].clone()
+    red2 = GradAllReducer(mods)
+    red2.step()
+    assert torch.allclose(layerwise, red2.flat, rtol=0, atol=1e-7)
+    # an incomplete backward must be reported, not silently reduced
+    red.on_layer(0, "dynamic_itr_l2", grads[0])
+    try:
+        red.wait()
+        ok = False
+    except RuntimeError:
+        ok = True
+    for w in red._works:               # (drain the collective of the deliberately incomplete round)
+        w.wait()
+    q.put((rank, layerwise.tolist(), ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_layerwise_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_layerwise_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]                     # both ranks hold the same averaged bucket
+    assert res[0][2] and res[1][2]

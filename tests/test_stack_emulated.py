@@ -211,3 +211,29 @@ def test_emulated_run_pair_equals_separate_calls(emulated):
     assert ga.keys() == gb.keys()
     for k in ga:
         assert torch.equal(ga[k], gb[k]), k
+
+
+def test_emulated_layer_hooks_deliver_every_live_gradient(emulated):
+    """GradAllReducer.install(): the stack's backward hands over each routing layer's finished gradients (last
+    layer first); after wait() the flat bucket equals the .grad of every live parameter."""
+    from d2r_b200.dp import GradAllReducer
+    from d2r_b200.interaction import InteractionModule, Reversed_InteractionModule, run_pair
+    torch.manual_seed(3)
+    mt = InteractionModule(make_args(), 3, 6, 128)
+    mi = Reversed_InteractionModule(make_args(), 3, 6, 128)
+    red = GradAllReducer([mt, mi])
+    order = []
+    red.install()
+    orig = red.on_layer
+    red.on_layer = lambda m, layer, grads: (order.append((m, layer)), orig(m, layer, grads))[1]
+    red.install()                      # re-register so that the wrapped callback is the one installed
+    text, image = O.make_inputs(INPUT_SEED_BASE + 2, 2, 6, 5)
+    (o1, s1), (o2, s2) = run_pair(mt, mi, text.requires_grad_(True), image.requires_grad_(True))
+    (o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()).backward()
+    red.wait()
+    assert order == [(0, "dynamic_itr_l2"), (0, "dynamic_itr_l1.0"), (0, "dynamic_itr_l0"),
+                     (1, "dynamic_itr_l2"), (1, "dynamic_itr_l1.0"), (1, "dynamic_itr_l0")]
+    for name, p, v in zip(red.names, red.params, red._views):
+        assert p.grad is not None, name
+        assert torch.equal(v, p.grad), name
+    red.uninstall()
