@@ -200,6 +200,8 @@ def own_arm(args):
     import d2r_b200.lanes as LN
     if args.cell_lanes is not None:
         LN.CELL_LANES = max(1, args.cell_lanes)
+    if args.priority:
+        LN.PRIORITIZE_FIRST_BLOCK = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -510,6 +512,8 @@ def main():
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="layer-wise gradient all-reduces launched from inside the backward (GradAllReducer.install) "
                          "instead of one collective after it; measured equal at 2 GPUs in round 1, not the default")
+    ap.add_argument("--priority", action="store_true",
+                    help="run_pair with high stream priority for the first (text) stack")
     ap.add_argument("--cell-lanes", type=int, default=None,
                     help="CUDA streams per routing layer (default: d2r_b200.lanes.CELL_LANES; 1 = one stream)")
     ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")

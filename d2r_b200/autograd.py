@@ -70,6 +70,16 @@ def _bwd_one(rec, grads) -> List[Optional[Tensor]]:
     return res
 
 
+def _block_lanes(dev, n):
+    """Lanes of n concurrent blocks -> (lanes, index of block 0's lane).  With priorities, every block runs on a
+    side stream (the caller's stream only forks and joins): block 0 -- the text stack under run_pair, twice the
+    work of the image stack and therefore the critical chain -- gets high-priority streams, so its CTAs are
+    scheduled first whenever SMs free up and the other block fills what is left."""
+    if n > 1 and LN.PRIORITIZE_FIRST_BLOCK:
+        return LN.fork(dev, n + 1, "blocks", priorities=[0, -1] + [0] * (n - 1)), 1
+    return LN.fork(dev, n, "blocks"), 0
+
+
 class _BlocksFn(torch.autograd.Function):
     """N independent blocks as ONE autograd node.  With N > 1 the blocks are issued on separate CUDA streams:
     their kernels fill each other's partial waves and sub-148-CTA launches.  Each lane allocates its temporaries
@@ -81,11 +91,11 @@ class _BlocksFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, specs, *tensors):
         dev = next(t.device for t in tensors if t is not None)
-        lanes = LN.fork(dev, len(specs), "blocks")
+        lanes, first = _block_lanes(dev, len(specs))
         recs, all_outs, off = [], [], 0
         for i, spec in enumerate(specs):
             n = spec[0] + len(spec[1])
-            with lanes.lane(i):
+            with lanes.lane(first + i):
                 outs, rec = _fwd_one(spec, tensors[off:off + n])
             off += n
             recs.append(rec)
@@ -102,12 +112,12 @@ class _BlocksFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         recs = ctx.recs
-        lanes = LN.fork(ctx.dev, len(recs), "blocks")
+        lanes, first = _block_lanes(ctx.dev, len(recs))
         res: List[Optional[Tensor]] = [None]
         off = 0
         for i, rec in enumerate(recs):
             n = len(rec["out_meta"])
-            with lanes.lane(i):
+            with lanes.lane(first + i):
                 res += _bwd_one(rec, grads[off:off + n])
             off += n
         lanes.join()

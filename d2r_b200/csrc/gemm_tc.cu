@@ -403,8 +403,8 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
     if (bn == 256) {
       const long long work = 1LL * ((a.m + 255) / 256) * ((a.n + 255) / 256) * split_k * a.batch;
       // enough 256x256 tiles to occupy the 74 CTA pairs, and a shape where halving the B fill pays (measured:
-      // long k, wide n or very tall m; the 12800-row K=768 projections are faster on single-CTA tiles)
-      pair = !softmax_epi && work >= 32 && (a.k >= 1536 || a.n >= 1536 || a.m >= 16384);
+      // long k, wide n or tall m -- 12800-row K=768 projection: 25.6 us on pairs, 27.5 us on single-CTA tiles)
+      pair = !softmax_epi && work >= 32 && (a.k >= 1536 || a.n >= 1536 || a.m >= 8192);
     }
   }
   D2R_CHECK_ARG(bn == 64 || bn == 128 || bn == 192 || bn == 256, "gemm: tile_n %d unsupported", bn);

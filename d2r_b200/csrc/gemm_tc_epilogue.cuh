@@ -353,41 +353,63 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
             }
           }
         } else {
+          // P of this warp's <= 2 chunks is fetched once and kept packed (bf16, 32 registers) across the exchange
           float part = 0.f;
-#pragma unroll 1
-          for (int c = cb; c < ce; ++c) {            // pass 1: this warp's share of sum_j dP_j P_j
-            uint32_t ra[32];
-            tmem_ld32(taddr + c * 32, ra);
-            tmem_ld_wait();
-            if (row_ok) {
+          uint4 pk[2][4];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {           // pass 1: this warp's share of sum_j dP_j P_j
+            const int c = cb + cc;
+            if (c < ce) {
+              uint32_t ra[32];
+              tmem_ld32(taddr + c * 32, ra);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float pr[8];
-                ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+                if (row_ok) {
+                  ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) part = fmaf(p.alpha * __uint_as_float(ra[g * 8 + i]), pr[i], part);
+                  for (int i = 0; i < 8; ++i) pr[i] = 0.f;
+                }
+                pk[cc][g] = pack8_bf16(pr);          // exact: P is bf16 in memory
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[cc][g]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __bfloat1622float2(h[i]);
+                  part = fmaf(p.alpha * __uint_as_float(ra[g * 8 + 2 * i]), f.x, part);
+                  part = fmaf(p.alpha * __uint_as_float(ra[g * 8 + 2 * i + 1]), f.y, part);
+                }
               }
             }
           }
           xch[lane] = part;
           pair_barrier(q);
           const float tot = part + xch_peer[lane];
-#pragma unroll 1
-          for (int c = cb; c < ce; ++c) {            // pass 2: dS = P * (alpha dP - total)
-            uint32_t ra[32];
-            float v[32], d[32];
-            tmem_ld32(taddr + c * 32, ra);
-            tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float pr[8];
-              if (row_ok) ld_group(rrow + c * 32 + g * 8, pr, max(0, min(8, ncols - c * 32 - g * 8)));
+          for (int cc = 0; cc < 2; ++cc) {           // pass 2: dS = P * (alpha dP - total)
+            const int c = cb + cc;
+            if (c < ce) {
+              uint32_t ra[32];
+              float v[32], d[32];
+              tmem_ld32(taddr + c * 32, ra);
+              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[g * 8 + i] = row_ok ? pr[i] * (p.alpha * __uint_as_float(ra[g * 8 + i]) - tot) : 0.f;
+              for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[cc][g]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __bfloat1622float2(h[i]);
+                  v[g * 8 + 2 * i] = f.x * (p.alpha * __uint_as_float(ra[g * 8 + 2 * i]) - tot);
+                  v[g * 8 + 2 * i + 1] = f.y * (p.alpha * __uint_as_float(ra[g * 8 + 2 * i + 1]) - tot);
+                }
+              }
+              if (use_tma) tma_store_row32<CT>(tmC, stage, lane, v, c * 32, row0, tc.zi, tc.zo);
+              else if (row_ok) direct_store<CT, 0>(p, crow, c2row, c * 32, v, d);
             }
-            if (use_tma) tma_store_row32<CT>(tmC, stage, lane, v, c * 32, row0, tc.zi, tc.zo);
-            else if (row_ok) direct_store<CT, 0>(p, crow, c2row, c * 32, v, d);
           }
         }
       } else {

@@ -24,9 +24,11 @@ class Lanes:
     """``n`` lanes forked from the current stream: lane 0 IS the current stream, lanes 1..n-1 are cached side
     streams private to (device, parent stream, fork site), so nested forks (a stack inside run_pair) never share streams."""
 
-    _side: Dict[Tuple[int, int, str, int], "torch.cuda.Stream"] = {}
+    _side: Dict[Tuple[int, int, str, int, int], "torch.cuda.Stream"] = {}
 
-    def __init__(self, device: torch.device, n: int, tag: str = ""):
+    def __init__(self, device: torch.device, n: int, tag: str = "", priorities=None):
+        """``priorities[i]`` (CUDA stream priority, -1 = high, 0 = default) of side lane i; default: the
+        priority of the caller's stream, so nested forks inherit it."""
         self.n = n
         self.cur = None
         self.streams: List = [None]
@@ -35,10 +37,11 @@ class Lanes:
         self.cur = torch.cuda.current_stream(device)
         idx = device.index if device.index is not None else torch.cuda.current_device()
         for i in range(1, n):
-            key = (idx, self.cur.cuda_stream, tag, i)
+            prio = self.cur.priority if priorities is None else priorities[i]
+            key = (idx, self.cur.cuda_stream, tag, i, prio)
             st = Lanes._side.get(key)
             if st is None:
-                st = Lanes._side[key] = torch.cuda.Stream(device=device)
+                st = Lanes._side[key] = torch.cuda.Stream(device=device, priority=prio)
             self.streams.append(st)
         # fork NOW, before lane 0 puts any work on the caller's stream: a later wait would order the side
         # streams behind that work and serialise everything
@@ -82,13 +85,15 @@ class NoLanes:
 # Concurrency switches (read at every call): ENABLED=False puts every launch on the caller's stream.
 ENABLED = True
 CELL_LANES = 4      # lanes per routing layer: [GLAC + GESC + routers | IMRC | CMRC | CRCMC]
+PRIORITIZE_FIRST_BLOCK = False  # run_pair: high stream priority for the first (text, heavier) stack -- measured
+                                # neutral (23.2 vs 23.1 ms), off
 FWD_LANES = True    # (bring-up switches: cell lanes in the forward / backward pass)
 BWD_LANES = True
 
 
-def fork(device: torch.device, n: int, tag: str = ""):
+def fork(device: torch.device, n: int, tag: str = "", priorities=None):
     """``tag`` names the fork site: forks at different sites under the same parent stream get different side
     streams (run_pair's second stack must not share a stream with a cell lane of the first)."""
     if not ENABLED or n <= 1 or device.type != "cuda":
         return NoLanes()
-    return Lanes(device, n, tag)
+    return Lanes(device, n, tag, priorities)

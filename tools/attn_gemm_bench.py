@@ -42,6 +42,11 @@ def main():
                   a_str=(Lq * 3 * D, dh), b_str=(Lc * 3 * D, dh), c_str=(H * Lq * Lcp, Lq * Lcp), alpha=0.14)
         t = timeit(lambda: K.gemm(qkv, qkv[:, :, D:], P, epilogue=L.EPI_SOFTMAX, **kw), flush)
         print(f"self scores+softmax L={Lq}: {t:7.1f} us", flush=True)
+        dS = torch.empty_like(P)
+        kwb = dict(kw, alpha=1.0)
+        t = timeit(lambda: K.gemm(qkv, qkv[:, :, 2 * D:], dS, epilogue=L.EPI_SOFTMAX_BWD, residual=P, ldr=Lcp,
+                                  r_str=(H * Lq * Lcp, Lq * Lcp), **kwb), flush)
+        print(f"self dP+softmax_bwd L={Lq}: {t:7.1f} us", flush=True)
         t = timeit(lambda: K.gemm(qkv, qkv[:, :, D:], S, **kw), flush)
         t2 = timeit(lambda: K.softmax_fwd(S, Lc, 1.0, bf), flush)
         print(f"self scores (fp32 S) L={Lq}: {t:7.1f} us  + softmax kernel {t2:7.1f} us", flush=True)
