@@ -514,11 +514,16 @@ def main():
                          "instead of one collective after it; measured equal at 2 GPUs in round 1, not the default")
     ap.add_argument("--priority", action="store_true",
                     help="run_pair with high stream priority for the first (text) stack")
+    ap.add_argument("--batch-per-gpu", type=int, default=None,
+                    help="diagnostic only: override the per-GPU batch (the benchmark configuration is 256)")
     ap.add_argument("--cell-lanes", type=int, default=None,
                     help="CUDA streams per routing layer (default: d2r_b200.lanes.CELL_LANES; 1 = one stream)")
     ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.batch_per_gpu:
+        global BATCH_PER_GPU
+        BATCH_PER_GPU = args.batch_per_gpu
     if args.cpu_sample:
         r = run_cpu_reference(steps=4, warmup=1)
         emit({"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]})

@@ -84,7 +84,7 @@ class NoLanes:
 
 # Concurrency switches (read at every call): ENABLED=False puts every launch on the caller's stream.
 ENABLED = True
-CELL_LANES = 4      # lanes per routing layer: [GLAC + GESC + routers | IMRC | CMRC | CRCMC]
+CELL_LANES = 5      # lanes per routing layer: [K/V + GLAC | IMRC | CMRC | CRCMC | routers + GESC]
 PRIORITIZE_FIRST_BLOCK = False  # run_pair: high stream priority for the first (text, heavier) stack -- measured
                                 # neutral (23.2 vs 23.1 ms), off
 FWD_LANES = True    # (bring-up switches: cell lanes in the forward / backward pass)

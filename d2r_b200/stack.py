@@ -564,15 +564,19 @@ def layer_forward(env: Env, pre: str, xs: Sequence[Tensor], z: Tensor, pooled: T
         lanes.catch_up(3)
         with lanes.lane(3):
             crcmc_out, crcmc_sv = _crcmc_fwd(env, pre + ".crcmc", xs[4], kv, 2)
-    norm, gate, rsv = _routers_fwd(env, routers, pooled, n_out, final)
+    # lane 4: the [B,768]-vector work (routers, GESC) -- a dozen latency-bound launches that would otherwise
+    # lengthen lane 0, the longest chain of the layer
+    with lanes.lane(4):
+        norm, gate, rsv = _routers_fwd(env, routers, pooled, n_out, final)
+        if Kc > 4:
+            gesc_out, gesc_sv = _gesc_fwd(env, pre + ".gesc", xs[5], z)
     st = dict(xs=list(xs), z=z, kv=kv, router=rsv, norm=norm, gate=gate, final=final, Kc=Kc, imrc=imrc_sv,
               cmrc=cmrc_sv)
     glac_out, st["glac"] = _glac_fwd(env, pre + ".glac", xs[1], z, kv, 0)
     full: List[Optional[Tensor]] = [xs[0], None, imrc_out, cmrc_out]
     bvec: List[Optional[Tensor]] = [None, glac_out, None, None]
     if Kc > 4:
-        st["crcmc"] = crcmc_sv
-        gesc_out, st["gesc"] = _gesc_fwd(env, pre + ".gesc", xs[5], z)
+        st["crcmc"], st["gesc"] = crcmc_sv, gesc_sv
         full += [crcmc_out, None]
         bvec += [None, gesc_out]
     lanes.join()
@@ -606,7 +610,8 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     if Kc > 4:
         with lanes.lane(3):
             d_xs[4] = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], None)
-    d_pooled = _routers_bwd(env, [f"{pre}.{cn}.router" for cn in cells], st["router"], d_norm, final)
+    with lanes.lane(4):
+        d_pooled = _routers_bwd(env, [f"{pre}.{cn}.router" for cn in cells], st["router"], d_norm, final)
     if shared_input:
         # one input tensor feeds every cell: GLAC folds the RIC gradient in as its residual, GESC adds its
         # row-0 gradient on top, the other cells' gradients are summed after the join
