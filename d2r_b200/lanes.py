@@ -61,6 +61,20 @@ class Lanes:
         if i:
             self.streams[i].wait_stream(self.cur)
 
+    def mark(self, i: int):
+        """Event at the current tail of lane i (None for lane 0): lets the caller's stream wait for the work issued
+        on that lane SO FAR without waiting for what is issued on it later (see wait_mark)."""
+        i %= max(self.n, 1)
+        if i == 0:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.streams[i])
+        return ev
+
+    def wait_mark(self, ev) -> None:
+        if ev is not None:
+            self.cur.wait_event(ev)
+
     def join(self) -> None:
         for st in self.streams[1:]:
             self.cur.wait_stream(st)
@@ -78,13 +92,19 @@ class NoLanes:
     def catch_up(self, i: int) -> None:
         pass
 
+    def mark(self, i: int):
+        return None
+
+    def wait_mark(self, ev) -> None:
+        pass
+
     def join(self) -> None:
         pass
 
 
 # Concurrency switches (read at every call): ENABLED=False puts every launch on the caller's stream.
 ENABLED = True
-CELL_LANES = 5      # lanes per routing layer: [K/V + GLAC | IMRC | CMRC | CRCMC | routers + GESC]
+CELL_LANES = 5      # lanes per routing layer: [K/V + GLAC local | IMRC | CMRC | CRCMC | routers + GESC + GLAC global]
 PRIORITIZE_FIRST_BLOCK = False  # run_pair: high stream priority for the first (text, heavier) stack -- measured
                                 # neutral (23.2 vs 23.1 ms), off
 FWD_LANES = True    # (bring-up switches: cell lanes in the forward / backward pass)

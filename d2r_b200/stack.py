@@ -162,8 +162,9 @@ def _row0_fwd(env: Env, xfull: Tensor, name: str) -> Tensor:
     return out
 
 
-def _row0_bwd(env: Env, d_vec: Tensor, y_vec: Tensor, xfull: Tensor, name: str, dx_full: Tensor) -> None:
-    """d_vec: fp32 gradient w.r.t. the tanh output; accumulates into row 0 of every sample of dx_full."""
+def _row0_bwd_params(env: Env, d_vec: Tensor, y_vec: Tensor, xfull: Tensor, name: str):
+    """Backward of a CLS pooler up to (not including) the input gradient: tanh', bias and weight gradients.
+    d_vec: fp32 gradient w.r.t. the tanh output.  Returns (dz in the compute dtype, staged W) for _row0_bwd_apply."""
     B, Ln, D = xfull.shape
     dz, db = K.bias_act_bwd(d_vec, y_vec, L.ACT_TANH, True, True)
     dzc = dz if env.cd == torch.float32 else K.cast(dz, env.cd)
@@ -172,7 +173,19 @@ def _row0_bwd(env: Env, d_vec: Tensor, y_vec: Tensor, xfull: Tensor, name: str, 
     K.gemm(dzc, xfull, dW, m=D, n=D, k=B, lda=D, ldb=Ln * D, ldc=D, a_mn=True, b_mn=True)
     env.grad(name + ".weight", dW)
     env.grad(name + ".bias", db)
+    return dzc, W
+
+
+def _row0_bwd_apply(pending, dx_full: Tensor) -> None:
+    """dx_full[:, 0, :] += dz W (read-modify-write of row 0 of every sample)."""
+    dzc, W = pending
+    B, Ln, D = dx_full.shape
     K.gemm(dzc, W, dx_full, m=B, n=D, k=D, lda=D, ldb=D, ldc=Ln * D, b_mn=True, residual=dx_full, ldr=Ln * D)
+
+
+def _row0_bwd(env: Env, d_vec: Tensor, y_vec: Tensor, xfull: Tensor, name: str, dx_full: Tensor) -> None:
+    """d_vec: fp32 gradient w.r.t. the tanh output; accumulates into row 0 of every sample of dx_full."""
+    _row0_bwd_apply(_row0_bwd_params(env, d_vec, y_vec, xfull, name), dx_full)
 
 
 def _small_fwd(env: Env, x32: Tensor, name: str, act: int = L.ACT_NONE):
@@ -327,15 +340,19 @@ def _cma_bwd(env: Env, name: str, x: Tensor, kv: _KV, i: int, saved, dC: Tensor,
 
 
 # ----------------------------------------------------------------------------- cells
-def _glac_fwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int):
-    B, Lq, D = x.shape
+def _glac_local_fwd(env: Env, c: str, x: Tensor, kv: _KV, ki: int):
+    """Token-level half of GLAC (Cells.py:149-158): sim_local = fc_1(l2norm(fc_sim_tranloc((x - ctx)^2)))."""
     d1 = torch.empty_like(x)
     sl, cma = _cma_fwd(env, c + ".CrossModalAlignment", x, kv, ki, residual=x, epilogue=L.EPI_SQDIFF, c2=d1)
     t1 = K.linear(sl, env.W(c + ".fc_sim_tranloc"), env.b(c + ".fc_sim_tranloc"))
     n1, rn1 = K.l2norm_fwd(t1)
     del t1
     t2 = K.linear(n1, env.W(c + ".fc_1"), env.b(c + ".fc_1"))                  # sim_local [B,Lq,D]
-    # global similarity (fp32, [B,D])
+    return t2, dict(cma=cma, d1=d1, sl=sl, n1=n1, rn1=rn1, t2=t2)
+
+
+def _glac_global_fwd(env: Env, c: str, x: Tensor, z: Tensor):
+    """[B,D] half of GLAC (Cells.py:159-163): sim_global = fc_2(l2norm(fc_sim_tranglo((t0 - i0)^2))), fp32."""
     t0 = _row0_fwd(env, x, c + ".text_cls_pool.dense")
     i0 = _row0_fwd(env, z, c + ".image_cls_pool.dense")
     dg = K.axpby(t0, i0, 1.0, -1.0)
@@ -344,21 +361,30 @@ def _glac_fwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int):
     ng, rng = K.l2norm_fwd(g1)
     sg, ng_c = _small_fwd(env, ng, c + ".fc_2")                                # sim_global [B,D]
     sgc = sg if env.cd == torch.float32 else K.cast(sg, env.cd)
+    return sgc, dict(t0=t0, i0=i0, dg=dg, sq_c=sq_c, ng=ng, ng_c=ng_c, rng=rng, sgc=sgc)
+
+
+def _glac_saf_fwd(env: Env, c: str, sgc: Tensor, t2: Tensor):
+    """Attention filtration over [sim_global ; sim_local] (XModules.py:380-384) -> out fp32 [B,D]."""
     s = c + ".SAF_module"
     P = env.P
     nbt = P.get(s + ".bn.num_batches_tracked")
-    out, saf = K.saf_fwd(sgc, t2, P[s + ".attn_sim_w.weight"].detach().view(-1), P[s + ".attn_sim_w.bias"].detach(),
-                         P[s + ".bn.weight"].detach(), P[s + ".bn.bias"].detach(), P[s + ".bn.running_mean"],
-                         P[s + ".bn.running_var"], nbt, env.training)
-    saved = dict(cma=cma, d1=d1, sl=sl, n1=n1, rn1=rn1, t2=t2, t0=t0, i0=i0, dg=dg, sq_c=sq_c, ng=ng, ng_c=ng_c,
-                 rng=rng, sgc=sgc, saf=saf)
+    return K.saf_fwd(sgc, t2, P[s + ".attn_sim_w.weight"].detach().view(-1), P[s + ".attn_sim_w.bias"].detach(),
+                     P[s + ".bn.weight"].detach(), P[s + ".bn.bias"].detach(), P[s + ".bn.running_mean"],
+                     P[s + ".bn.running_var"], nbt, env.training)
+
+
+def _glac_fwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int):
+    t2, saved = _glac_local_fwd(env, c, x, kv, ki)
+    sgc, gsv = _glac_global_fwd(env, c, x, z)
+    out, saf = _glac_saf_fwd(env, c, sgc, t2)
+    saved.update(gsv)
+    saved["saf"] = saf
     return out, saved
 
 
-def _glac_bwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int, sv, d_out: Tensor, add: Optional[Tensor],
-              dz_row0: Tensor) -> Tensor:
-    """d_out: fp32 [B,D].  Returns dx [B,Lq,D]; the image_cls_pool gradient goes to row 0 of dz_row0."""
-    B, Lq, D = x.shape
+def _glac_saf_bwd(env: Env, c: str, sv, d_out: Tensor):
+    """d_out: fp32 [B,D] -> (d sim_global [B,D] compute dtype, d sim_local [B,Lq,D])."""
     s = c + ".SAF_module"
     P = env.P
     d_sgc, d_t2, d_w, d_b, d_bnw, d_bnb = K.saf_bwd(
@@ -369,23 +395,41 @@ def _glac_bwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int, sv, d_ou
     env.grad(s + ".attn_sim_w.bias", d_b)
     env.grad(s + ".bn.weight", d_bnw)
     env.grad(s + ".bn.bias", d_bnb)
-    # local branch
+    return d_sgc, d_t2
+
+
+def _glac_local_bwd(env: Env, c: str, x: Tensor, kv: _KV, ki: int, sv, d_t2: Tensor, add: Optional[Tensor]) -> Tensor:
+    B, Lq, D = x.shape
     dn1 = lin_bwd(env, d_t2.view(B * Lq, D), sv["n1"], D, env.W(c + ".fc_1"), [c + ".fc_1"])
     dt1 = K.l2norm_bwd(sv["n1"].view(B * Lq, D), dn1, sv["rn1"])
     dsl = lin_bwd(env, dt1, sv["sl"], D, env.W(c + ".fc_sim_tranloc"), [c + ".fc_sim_tranloc"])
     g, gx = K.sqdiff_bwd(dsl, sv["d1"].view(B * Lq, D), add.view(B * Lq, D) if add is not None else None,
                          want_gx=True)
     # d1 = x - ctx: d ctx = -g (sign folded into the attention backward), dx gets +g (+ add)
-    dx = _cma_bwd(env, c + ".CrossModalAlignment", x, kv, ki, sv["cma"], g.view(B, Lq, D), -1.0, gx)
-    # global branch
+    return _cma_bwd(env, c + ".CrossModalAlignment", x, kv, ki, sv["cma"], g.view(B, Lq, D), -1.0, gx)
+
+
+def _glac_global_bwd(env: Env, c: str, x: Tensor, z: Tensor, sv, d_sgc: Tensor):
+    """-> pending row-0 updates (for _row0_bwd_apply): [into dx of this cell, into dz]."""
     dsg = d_sgc if env.cd == torch.float32 else K.cast(d_sgc, torch.float32)
     dng = _small_bwd(env, dsg, sv["ng_c"], c + ".fc_2")
     dg1 = K.l2norm_bwd(sv["ng"], dng, sv["rng"])
     dsq = _small_bwd(env, dg1, sv["sq_c"], c + ".fc_sim_tranglo")
     ddg = K.mul(dsq, sv["dg"], 2.0)
-    _row0_bwd(env, ddg, sv["t0"], x, c + ".text_cls_pool.dense", dx)
+    px = _row0_bwd_params(env, ddg, sv["t0"], x, c + ".text_cls_pool.dense")
     nddg = K.axpby(ddg, None, -1.0, 0.0)
-    _row0_bwd(env, nddg, sv["i0"], z, c + ".image_cls_pool.dense", dz_row0)
+    pz = _row0_bwd_params(env, nddg, sv["i0"], z, c + ".image_cls_pool.dense")
+    return [px, pz]
+
+
+def _glac_bwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int, sv, d_out: Tensor, add: Optional[Tensor],
+              dz_row0: Tensor) -> Tensor:
+    """d_out: fp32 [B,D].  Returns dx [B,Lq,D]; the image_cls_pool gradient goes to row 0 of dz_row0."""
+    d_sgc, d_t2 = _glac_saf_bwd(env, c, sv, d_out)
+    dx = _glac_local_bwd(env, c, x, kv, ki, sv, d_t2, add)
+    px, pz = _glac_global_bwd(env, c, x, z, sv, d_sgc)
+    _row0_bwd_apply(px, dx)
+    _row0_bwd_apply(pz, dz_row0)
     return dx
 
 
@@ -484,15 +528,23 @@ def _gesc_fwd(env: Env, c: str, x: Tensor, z: Tensor):
     return out, dict(t=t, i=i, u_c=u_c, h1=h1, h1_c=h1_c, g=g)
 
 
-def _gesc_bwd(env: Env, c: str, x: Tensor, z: Tensor, sv, d_out: Tensor, dx_row0: Tensor, dz_row0: Tensor) -> None:
-    """d_out fp32 [B,D]; both pooler gradients are accumulated into row 0 of dx_row0 / dz_row0."""
+def _gesc_bwd_params(env: Env, c: str, x: Tensor, z: Tensor, sv, d_out: Tensor):
+    """d_out fp32 [B,D] -> pending row-0 updates (for _row0_bwd_apply): [into dx of this cell, into dz]."""
     d_gl, d_t, d_i = K.gate_fuse_bwd(d_out, sv["g"], sv["t"], sv["i"])
     dh1 = _small_bwd(env, d_gl, sv["h1_c"], c + ".fc_mlp.2")
     du = _small_bwd(env, dh1, sv["u_c"], c + ".fc_mlp.0", y=sv["h1"], act=L.ACT_TANH)
     d_t = K.axpby(d_t, du, 1.0, 1.0)
     d_i = K.axpby(d_i, du, 1.0, 1.0)
-    _row0_bwd(env, d_t, sv["t"], x, c + ".text_cls_pool.dense", dx_row0)
-    _row0_bwd(env, d_i, sv["i"], z, c + ".image_cls_pool.dense", dz_row0)
+    px = _row0_bwd_params(env, d_t, sv["t"], x, c + ".text_cls_pool.dense")
+    pz = _row0_bwd_params(env, d_i, sv["i"], z, c + ".image_cls_pool.dense")
+    return [px, pz]
+
+
+def _gesc_bwd(env: Env, c: str, x: Tensor, z: Tensor, sv, d_out: Tensor, dx_row0: Tensor, dz_row0: Tensor) -> None:
+    """d_out fp32 [B,D]; both pooler gradients are accumulated into row 0 of dx_row0 / dz_row0."""
+    px, pz = _gesc_bwd_params(env, c, x, z, sv, d_out)
+    _row0_bwd_apply(px, dx_row0)
+    _row0_bwd_apply(pz, dz_row0)
 
 
 # ----------------------------------------------------------------------------- routers
@@ -549,12 +601,22 @@ def layer_forward(env: Env, pre: str, xs: Sequence[Tensor], z: Tensor, pooled: T
     cells = CELLS6[:Kc]
     n_out = 1 if final else Kc
     routers = [f"{pre}.{cn}.router" for cn in cells]
-    # The cells read the same layer input and are independent until the aggregation: one lane (CUDA stream)
-    # each for the three token-level cells, lane 0 (the caller's stream) for the K/V projections they share,
-    # the routers and the two [B,D] global cells.
+    # The cells read the same layer input and are independent until the aggregation.  Lanes (CUDA streams):
+    #   0 (caller's)  K/V projections of the context (shared by the cross-modal cells), GLAC's token-level half,
+    #                 the attention filtration that joins GLAC's two halves
+    #   1, 2, 3       IMRC, CMRC, CRCMC
+    #   4             everything that lives on [B,768] vectors: GLAC's global half, the routers, GESC -- some
+    #                 two dozen latency-bound launches that would otherwise lengthen lane 0, the longest chain
     lanes = LN.fork(z.device, LN.CELL_LANES if LN.FWD_LANES else 1, "cells")
     with lanes.lane(1):
         imrc_out, imrc_sv = _imrc_fwd(env, pre + ".imrc.sa", xs[2])
+    with lanes.lane(4):
+        sgc, glac_sv = _glac_global_fwd(env, pre + ".glac", xs[1], z)
+    sgc_ready = lanes.mark(4)
+    with lanes.lane(4):
+        norm, gate, rsv = _routers_fwd(env, routers, pooled, n_out, final)
+        if Kc > 4:
+            gesc_out, gesc_sv = _gesc_fwd(env, pre + ".gesc", xs[5], z)
     kv = _KV(env, z, [pre + ".glac.CrossModalAlignment", pre + ".cmrc.refine.CrossModalAlignment"] +
              ([pre + ".crcmc.CrossModalAlignment"] if Kc > 4 else []))
     lanes.catch_up(2)
@@ -564,15 +626,12 @@ def layer_forward(env: Env, pre: str, xs: Sequence[Tensor], z: Tensor, pooled: T
         lanes.catch_up(3)
         with lanes.lane(3):
             crcmc_out, crcmc_sv = _crcmc_fwd(env, pre + ".crcmc", xs[4], kv, 2)
-    # lane 4: the [B,768]-vector work (routers, GESC) -- a dozen latency-bound launches that would otherwise
-    # lengthen lane 0, the longest chain of the layer
-    with lanes.lane(4):
-        norm, gate, rsv = _routers_fwd(env, routers, pooled, n_out, final)
-        if Kc > 4:
-            gesc_out, gesc_sv = _gesc_fwd(env, pre + ".gesc", xs[5], z)
+    t2, glac_local = _glac_local_fwd(env, pre + ".glac", xs[1], kv, 0)
+    lanes.wait_mark(sgc_ready)
+    glac_out, glac_sv["saf"] = _glac_saf_fwd(env, pre + ".glac", sgc, t2)
+    glac_sv.update(glac_local)
     st = dict(xs=list(xs), z=z, kv=kv, router=rsv, norm=norm, gate=gate, final=final, Kc=Kc, imrc=imrc_sv,
-              cmrc=cmrc_sv)
-    glac_out, st["glac"] = _glac_fwd(env, pre + ".glac", xs[1], z, kv, 0)
+              cmrc=cmrc_sv, glac=glac_sv)
     full: List[Optional[Tensor]] = [xs[0], None, imrc_out, cmrc_out]
     bvec: List[Optional[Tensor]] = [None, glac_out, None, None]
     if Kc > 4:
@@ -600,8 +659,9 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     dz_rows = torch.zeros_like(z) if dz_acc is None else dz_acc
     kv.grads()                                       # allocated on the caller's stream, before the fork
     d_xs: List[Optional[Tensor]] = [None] * Kc
-    # same lanes as the forward (a cell's saved activations were allocated on its lane): the token-level cells
-    # run concurrently, lane 0 takes the routers' backward, GLAC and GESC (both touch row 0 of dz_rows)
+    # same lanes as the forward (a cell's saved activations were allocated on its lane).  The CLS-pooler gradients
+    # of GLAC and GESC are read-modify-writes of row 0 of tensors other lanes produce (this cell's dx, dz_rows):
+    # lane 4 computes everything up to them, they are applied after the join.
     lanes = LN.fork(z.device, LN.CELL_LANES if LN.BWD_LANES else 1, "cells")
     with lanes.lane(1):
         d_xs[2] = _imrc_bwd(env, pre + ".imrc.sa", xs[2], st["imrc"], d_full[2], None)
@@ -610,33 +670,39 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     if Kc > 4:
         with lanes.lane(3):
             d_xs[4] = _crcmc_bwd(env, pre + ".crcmc", xs[4], kv, 2, st["crcmc"], d_full[4], None)
+    d_sgc, d_t2 = _glac_saf_bwd(env, pre + ".glac", st["glac"], d_bvec[1])
+    lanes.catch_up(4)                                # lane 4 needs d_sgc
+    gesc_rows = None
     with lanes.lane(4):
+        glac_rows = _glac_global_bwd(env, pre + ".glac", xs[1], z, st["glac"], d_sgc)
         d_pooled = _routers_bwd(env, [f"{pre}.{cn}.router" for cn in cells], st["router"], d_norm, final)
-    if shared_input:
-        # one input tensor feeds every cell: GLAC folds the RIC gradient in as its residual, GESC adds its
-        # row-0 gradient on top, the other cells' gradients are summed after the join
-        acc = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], d_full[0], dz_rows)
         if Kc > 4:
-            _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], acc, dz_rows)
-        lanes.join()
+            gesc_rows = _gesc_bwd_params(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5])
+    # GLAC's token-level half; with one shared input tensor (layer 0) it folds the RIC gradient in as residual
+    dx_glac = _glac_local_bwd(env, pre + ".glac", xs[1], kv, 0, st["glac"], d_t2, d_full[0] if shared_input else None)
+    if not shared_input and Kc > 4:
+        d_xs[5] = torch.empty_like(xs[5]) if final else torch.zeros_like(xs[5])
+    lanes.join()
+    _row0_bwd_apply(glac_rows[0], dx_glac)
+    _row0_bwd_apply(glac_rows[1], dz_rows)
+    if shared_input:
+        # GESC adds its row-0 gradient on top of GLAC's dx, the other cells' gradients are summed in
+        acc = dx_glac
+        if Kc > 4:
+            _row0_bwd_apply(gesc_rows[0], acc)
+            _row0_bwd_apply(gesc_rows[1], dz_rows)
         for j in range(2, min(Kc, 5)):
             acc = K.axpby(acc, d_xs[j], 1.0, 1.0)
         d_xs = [acc]
     else:
-        d_xs[0] = d_full[0]
-        d_xs[1] = _glac_bwd(env, pre + ".glac", xs[1], z, kv, 0, st["glac"], d_bvec[1], None, dz_rows)
-        acc_mask = 0b1110
-        if Kc > 4:
-            d_xs[5] = torch.empty_like(xs[5]) if final else torch.zeros_like(xs[5])
-            acc_mask = 0b011110                      # cell 5 (GESC) has no full-size gradient yet: overwrite
-            if not final:
-                _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d_xs[5], dz_rows)
-        lanes.join()
+        d_xs[0], d_xs[1] = d_full[0], dx_glac
         if final:
-            # gated skip of the final layer (DynamicInteraction.py:108-111): touches only gated samples
-            K.gate_skip_bwd(d_outs[0], st["norm"], st["gate"], d_xs, acc_mask)
-            if Kc > 4:
-                _gesc_bwd(env, pre + ".gesc", xs[5], z, st["gesc"], d_bvec[5], d_xs[5], dz_rows)
+            # gated skip of the final layer (DynamicInteraction.py:108-111): touches only gated samples; cell 5
+            # (GESC) has no full-size gradient yet and is overwritten, the others are accumulated into
+            K.gate_skip_bwd(d_outs[0], st["norm"], st["gate"], d_xs, 0b011110 if Kc > 4 else 0b1110)
+        if Kc > 4:
+            _row0_bwd_apply(gesc_rows[0], d_xs[5])
+            _row0_bwd_apply(gesc_rows[1], dz_rows)
     del d_full, d_bvec                               # (kept alive until the join: read by the side lanes)
     dz = kv.backward(env, dz_rows)
     return d_xs, d_pooled, dz
