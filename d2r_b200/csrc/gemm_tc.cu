@@ -139,6 +139,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The prologue above touches no global data: under programmatic dependent launch it overlaps the tail of the
+  // previous kernel on the stream.  From here on every role reads or overwrites memory that kernel may still use.
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
@@ -296,6 +300,30 @@ int encode_operand(CUtensorMap* tm, const void* base, long long inner, long long
   return encode_map(tm, base, 2, inner, rows, bi, bo, ld, si, so, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may be scheduled while its
+// predecessor on the stream is still draining; it orders itself with griddepcontrol.wait after its prologue.
+// D2R_PDL=0 in the environment launches normally.
+template <typename Kern, typename... Args>
+cudaError_t launch_pdl(Kern kern, dim3 grid, int smem_bytes, cudaStream_t stream, const Args&... args) {
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("D2R_PDL");
+    use_pdl = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
               const TcParams& p, cudaStream_t stream) {
@@ -307,7 +335,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     attr_set = true;
   }
   long long grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<(unsigned)grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+  D2R_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmC2, p));
   count_launch();
   return check_launch("gemm_tc_kernel");
 }
@@ -339,7 +367,7 @@ int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     max_units = PAIRS == 1 ? num_sms() / 2 : max_clusters(kern, 2 * PAIRS, Tc2Cfg::SMEM_BYTES);
   }
   const long long units = p.num_tiles < max_units ? p.num_tiles : max_units;
-  kern<<<(unsigned)(2 * PAIRS * units), kTcThreads, Tc2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+  D2R_CUDA_OK(launch_pdl(kern, dim3((unsigned)(2 * PAIRS * units)), Tc2Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmC2, p));
   count_launch();
   return check_launch("gemm_tc2_kernel");
 }

@@ -83,6 +83,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                               // both CTAs' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                                    // (see gemm_tc_kernel: the prologue touched no global data)
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer (one per CTA)

@@ -176,6 +176,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // ===================================================================== cta_group::2 (CTA pair) variants
 namespace d2r {
 
+// Programmatic dependent launch.  pdl_trigger(): the grids that depend on this one may be scheduled now (they still
+// block in pdl_wait() until this grid has completed and flushed its memory); pdl_wait(): block until every grid
+// this one depends on has completed.  Both are no-ops for launches without the programmatic attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
