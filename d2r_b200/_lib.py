@@ -108,6 +108,8 @@ SYMBOLS = {
     "d2r_saf_bwd": (C.c_int, [C.POINTER(SafBwdArgs), _vp]),
     "d2r_gate_fuse_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "d2r_gate_fuse_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "d2r_js_div_fwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "d2r_js_div_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
 }
 
 

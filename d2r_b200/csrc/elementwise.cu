@@ -389,6 +389,87 @@ __global__ void __launch_bounds__(kThreads) gate_fuse_bwd_kernel(const float* __
   }
 }
 
+
+// ------------------------------------------------------------------ JS divergence of two row-softmaxes: block per row
+// XModules.py:32-41.  Two passes over the row for the softmax statistics of p and q, one for the terms.
+struct RowStats { float mp, mq, ip, iq; };   // row maxima and 1 / sum exp
+
+__device__ __forceinline__ RowStats js_row_stats(const float* pr, const float* qr, int cols, int get_softmax, float* sm) {
+  RowStats s{0.f, 0.f, 1.f, 1.f};
+  if (!get_softmax) return s;
+  float mp = -INFINITY, mq = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += kThreads) {
+    mp = fmaxf(mp, pr[c]);
+    mq = fmaxf(mq, qr[c]);
+  }
+  mp = block_reduce(mp, sm, true);
+  mq = block_reduce(mq, sm, true);
+  float sp = 0.f, sq = 0.f;
+  for (int c = threadIdx.x; c < cols; c += kThreads) {
+    sp += expf(pr[c] - mp);
+    sq += expf(qr[c] - mq);
+  }
+  sp = block_reduce(sp, sm, false);
+  sq = block_reduce(sq, sm, false);
+  s.mp = mp; s.mq = mq; s.ip = 1.f / sp; s.iq = 1.f / sq;
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads) js_div_fwd_kernel(const float* __restrict__ p, const float* __restrict__ q,
+                                                              int cols, int get_softmax, float scale,
+                                                              float* __restrict__ loss) {
+  __shared__ float sm[8];
+  const float* pr = p + (long long)blockIdx.x * cols;
+  const float* qr = q + (long long)blockIdx.x * cols;
+  const RowStats s = js_row_stats(pr, qr, cols, get_softmax, sm);
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < cols; c += kThreads) {
+    const float P = get_softmax ? expf(pr[c] - s.mp) * s.ip : pr[c];
+    const float Q = get_softmax ? expf(qr[c] - s.mq) * s.iq : qr[c];
+    const float lm = logf(0.5f * (P + Q));
+    if (P > 0.f) acc += P * (logf(P) - lm);            // xlogy semantics of KLDivLoss: 0 log 0 = 0
+    if (Q > 0.f) acc += Q * (logf(Q) - lm);
+  }
+  acc = block_reduce(acc, sm, false);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * scale);
+}
+
+__global__ void __launch_bounds__(kThreads) js_div_bwd_kernel(const float* __restrict__ p, const float* __restrict__ q,
+                                                              int cols, int get_softmax, float scale,
+                                                              const float* __restrict__ d_loss, float* __restrict__ dp,
+                                                              float* __restrict__ dq) {
+  __shared__ float sm[8];
+  const long long row = blockIdx.x;
+  const float* pr = p + row * cols;
+  const float* qr = q + row * cols;
+  const RowStats s = js_row_stats(pr, qr, cols, get_softmax, sm);
+  const float up = d_loss[0] * scale;
+  // d f / d P_j = (log P_j - log M_j) / 2 (the +1 of x log x cancels against the M terms); same for Q
+  float dotp = 0.f, dotq = 0.f;
+  for (int c = threadIdx.x; c < cols; c += kThreads) {
+    const float P = get_softmax ? expf(pr[c] - s.mp) * s.ip : pr[c];
+    const float Q = get_softmax ? expf(qr[c] - s.mq) * s.iq : qr[c];
+    const float lm = logf(0.5f * (P + Q));
+    const float gp = P > 0.f ? logf(P) - lm : 0.f;
+    const float gq = Q > 0.f ? logf(Q) - lm : 0.f;
+    dotp += P * gp;
+    dotq += Q * gq;
+  }
+  if (get_softmax) {
+    dotp = block_reduce(dotp, sm, false);
+    dotq = block_reduce(dotq, sm, false);
+  }
+  for (int c = threadIdx.x; c < cols; c += kThreads) {
+    const float P = get_softmax ? expf(pr[c] - s.mp) * s.ip : pr[c];
+    const float Q = get_softmax ? expf(qr[c] - s.mq) * s.iq : qr[c];
+    const float lm = logf(0.5f * (P + Q));
+    const float gp = P > 0.f ? logf(P) - lm : 0.f;
+    const float gq = Q > 0.f ? logf(Q) - lm : 0.f;
+    // through the softmax: dp_j = P_j (g_j - sum_k P_k g_k)
+    dp[row * cols + c] = up * (get_softmax ? P * (gp - dotp) : gp);
+    dq[row * cols + c] = up * (get_softmax ? Q * (gq - dotq) : gq);
+  }
+}
 }  // namespace
 
 // ======================================================================== C ABI
@@ -581,6 +662,26 @@ int d2r_gate_fuse_bwd(const float* d_out, const float* g, const float* t, const 
   gate_fuse_bwd_kernel<<<(unsigned)B, kThreads, 0, st>>>(d_out, g, t, i, d_gl, d_t, d_i, D);
   count_launch();
   return check_launch("gate_fuse_bwd_kernel");
+}
+
+int d2r_js_div_fwd(const float* p, const float* q, int64_t rows, int32_t cols, int32_t get_softmax, float* loss,
+                   void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(p && q && loss && cols >= 1 && rows >= 0, "js_div_fwd: bad arguments");
+  if (rows == 0) return D2R_OK;
+  js_div_fwd_kernel<<<(unsigned)rows, kThreads, 0, st>>>(p, q, cols, get_softmax, 0.5f / (float)rows, loss);
+  count_launch();
+  return check_launch("js_div_fwd_kernel");
+}
+
+int d2r_js_div_bwd(const float* p, const float* q, int64_t rows, int32_t cols, int32_t get_softmax,
+                   const float* d_loss, float* dp, float* dq, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(p && q && d_loss && dp && dq && cols >= 1 && rows >= 0, "js_div_bwd: bad arguments");
+  if (rows == 0) return D2R_OK;
+  js_div_bwd_kernel<<<(unsigned)rows, kThreads, 0, st>>>(p, q, cols, get_softmax, 0.5f / (float)rows, d_loss, dp, dq);
+  count_launch();
+  return check_launch("js_div_bwd_kernel");
 }
 
 }  // extern "C"

@@ -1,8 +1,8 @@
 """Mirror of the live parts of reference models/XModules.py: l1norm/l2norm :14-24, CrossModalAlignment
 :277-328 (live part :300-310; the reverse-attention / ContrastiveLoss branch :312-326 is dead work whose
 result every caller discards -- its parameters fc_1/fc_2 are kept for state_dict parity, the returned
-loss is a constant 0), AttentionFiltration :366-394.  ``js_div`` and ``Block`` (used by the backbone
-after the stack) stay plain PyTorch."""
+loss is a constant 0), AttentionFiltration :366-394, js_div :32-41 (fused kernel).  ``Block`` (used by the
+backbone after the stack) is not mirrored yet."""
 import math
 
 import numpy as np
@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from .. import stack as S
 from .. import kernels as K
+from .. import autograd as _A
 from ..autograd import run_block
 
 
@@ -25,14 +26,31 @@ def l1norm(X, dim, eps=1e-8):
     return torch.div(X, norm)
 
 
+class _JsDivFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, q, get_softmax):
+        pf, qf = p.detach().float().contiguous(), q.detach().float().contiguous()
+        ctx.save_for_backward(pf, qf)
+        ctx.get_softmax = get_softmax
+        ctx.dtypes = (p.dtype, q.dtype)
+        return K.js_div_fwd(pf, qf, get_softmax)
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        pf, qf = ctx.saved_tensors
+        dp, dq = K.js_div_bwd(pf, qf, d_loss.detach().float().contiguous(), ctx.get_softmax)
+        return dp.to(ctx.dtypes[0]), dq.to(ctx.dtypes[1]), None
+
+
 def js_div(p_output, q_output, get_softmax=True):
-    """reference models/XModules.py:32-41 (post-stack loss term; plain PyTorch)."""
-    kl = nn.KLDivLoss(reduction='batchmean')
-    if get_softmax:
-        p_output = F.softmax(p_output, dim=-1)
-        q_output = F.softmax(q_output, dim=-1)
-    log_mean_output = ((p_output + q_output) / 2).log()
-    return (kl(log_mean_output, p_output) + kl(log_mean_output, q_output)) / 2
+    """reference models/XModules.py:32-41: JS divergence between the row-softmaxes of two logit matrices
+    (``(sim_paths, sim_text)`` and ``(Reversed_sim_paths, sim_vision)`` at modeling_unimo.py:849); KLDivLoss
+    'batchmean' = sum over all elements / first dimension.  One fused kernel each way,
+    2-D CUDA inputs only, like the rest of the path."""
+    if p_output.dim() != 2 or p_output.shape != q_output.shape:
+        raise ValueError("d2r_b200.js_div: expects two [rows, cols] matrices of the same shape")
+    _A._require_cuda([p_output, q_output])
+    return _JsDivFn.apply(p_output, q_output, bool(get_softmax))
 
 
 def hidden_size_of(config) -> int:

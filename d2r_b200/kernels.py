@@ -262,6 +262,24 @@ def gate_fuse_bwd(d_out: Tensor, g: Tensor, t: Tensor, i: Tensor):
     return d_gl, d_t, d_i
 
 
+def js_div_fwd(p: Tensor, q: Tensor, get_softmax: bool = True) -> Tensor:
+    """JS divergence of two [rows, cols] fp32 logit matrices (XModules.py:32-41) -> fp32 scalar tensor."""
+    L.require_cuda(p, q)
+    rows, cols = p.shape
+    loss = torch.zeros((), device=p.device, dtype=torch.float32)
+    L.check(L.lib.d2r_js_div_fwd(p.data_ptr(), q.data_ptr(), rows, cols, int(get_softmax), loss.data_ptr(),
+                                 L.stream()), "js_div_fwd")
+    return loss
+
+
+def js_div_bwd(p: Tensor, q: Tensor, d_loss: Tensor, get_softmax: bool = True):
+    rows, cols = p.shape
+    dp, dq = torch.empty_like(p), torch.empty_like(q)
+    L.check(L.lib.d2r_js_div_bwd(p.data_ptr(), q.data_ptr(), rows, cols, int(get_softmax), d_loss.data_ptr(),
+                                 dp.data_ptr(), dq.data_ptr(), L.stream()), "js_div_bwd")
+    return dp, dq
+
+
 def router_head_fwd(hid: Tensor, w2: Sequence[Tensor], b2: Sequence[Tensor], n_out: int, final_layer: bool):
     """hid [K,B,H] fp32 (post-ReLU) -> raw, norm [B,n_out,K], gate [B,n_out] ([B,K] in the final layer)."""
     K_, B, H = hid.shape

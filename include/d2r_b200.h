@@ -223,6 +223,18 @@ int d2r_gate_fuse_fwd(const float* gl, const float* t, const float* i, float* g,
 int d2r_gate_fuse_bwd(const float* d_out, const float* g, const float* t, const float* i, float* d_gl,
                       float* d_t, float* d_i, int64_t B, int32_t D, void* stream);
 
+/* ---- (f, next) path-similarity loss ------------------------------------------------------
+ * XModules.py:32-41 js_div(p, q), called on (sim_paths, sim_text) and (Reversed_sim_paths, sim_vision),
+ * modeling_unimo.py:849.  p, q: fp32 [rows, cols] (row stride = cols).  With get_softmax != 0:
+ *   P = softmax_row(p), Q = softmax_row(q), M = (P + Q) / 2,
+ *   loss = ( sum P (log P - log M) + sum Q (log Q - log M) ) / (2 * rows)     (KLDivLoss 'batchmean')
+ * get_softmax == 0: p and q already are the probabilities.  `loss` is ONE fp32 value, ACCUMULATED (+=): zero
+ * it first.  The backward writes dp, dq = d_loss[0] * d loss / d p, d q (d_loss: device scalar). */
+int d2r_js_div_fwd(const float* p, const float* q, int64_t rows, int32_t cols, int32_t get_softmax, float* loss,
+                   void* stream);
+int d2r_js_div_bwd(const float* p, const float* q, int64_t rows, int32_t cols, int32_t get_softmax,
+                   const float* d_loss, float* dp, float* dq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -429,6 +429,17 @@ DEAD_PARAM_SUFFIXES = (".CrossModalAlignment.fc_1.weight", ".CrossModalAlignment
 ZERO_GRAD_SUFFIXES = (".CrossModalAlignment.key.bias", ".att_layer.linears.1.bias", ".crcmc.fc_2.bias")
 
 
+def js_div(p_output: torch.Tensor, q_output: torch.Tensor, get_softmax: bool = True) -> torch.Tensor:
+    """XModules.py:32-41 -- JS divergence as the reference writes it (KLDivLoss 'batchmean' on the log of the
+    mean distribution)."""
+    kl = torch.nn.KLDivLoss(reduction="batchmean")
+    if get_softmax:
+        p_output = torch.softmax(p_output, dim=-1)
+        q_output = torch.softmax(q_output, dim=-1)
+    log_mean_output = ((p_output + q_output) / 2).log()
+    return (kl(log_mean_output, p_output) + kl(log_mean_output, q_output)) / 2
+
+
 def is_zero_grad_param(name: str, training: bool) -> bool:
     """Parameters whose gradient is mathematically zero (softmax shift invariance of a key-projection bias;
     a bias in front of train-mode BatchNorm): both sides only hold rounding noise."""

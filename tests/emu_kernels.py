@@ -160,6 +160,28 @@ def gate_fuse_fwd(gl, t, i):
     return g, g * t + (1 - g) * i
 
 
+def _js_terms(p, q, get_softmax):
+    P = torch.softmax(p, -1) if get_softmax else p
+    Q = torch.softmax(q, -1) if get_softmax else q
+    lm = (0.5 * (P + Q)).log()
+    gp = torch.where(P > 0, P.clamp_min(1e-45).log() - lm, torch.zeros_like(P))
+    gq = torch.where(Q > 0, Q.clamp_min(1e-45).log() - lm, torch.zeros_like(Q))
+    return P, Q, gp, gq
+
+
+def js_div_fwd(p, q, get_softmax=True):
+    P, Q, gp, gq = _js_terms(p.float(), q.float(), get_softmax)
+    return ((P * gp).sum() + (Q * gq).sum()) * (0.5 / p.shape[0])
+
+
+def js_div_bwd(p, q, d_loss, get_softmax=True):
+    P, Q, gp, gq = _js_terms(p.float(), q.float(), get_softmax)
+    up = d_loss * (0.5 / p.shape[0])
+    if get_softmax:
+        return (up * P * (gp - (P * gp).sum(-1, keepdim=True)), up * Q * (gq - (Q * gq).sum(-1, keepdim=True)))
+    return up * gp, up * gq
+
+
 def gate_fuse_bwd(d_out, g, t, i):
     dg = d_out * (t - i)
     return g * (dg - (dg * g).sum(-1, keepdim=True)), d_out * g, d_out * (1 - g)

@@ -263,3 +263,27 @@ def test_gate_fuse():
     ref.backward(d_out.double())
     d_gl, d_t, d_i = K.gate_fuse_bwd(d_out, g, t, i)
     assert close(d_gl, gd.grad, 1e-4) and close(d_t, td.grad, 1e-5) and close(d_i, idd.grad, 1e-5)
+
+
+@pytest.mark.parametrize("rows,cols,get_softmax", [(256, 256, True), (8, 8, True), (33, 1000, True), (64, 64, False)])
+def test_js_div_vs_reference_formula(rows, cols, get_softmax):
+    """Fused JS-divergence kernels (XModules.py:32-41, the loss on sim_paths) vs the reference formula under torch
+    autograd in fp64; logits at the scale of sim_paths Grams (tens)."""
+    from d2r_b200.interaction.XModules import js_div
+    from oracle import d2r_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    a = torch.randn(rows, cols, device="cuda", generator=g) * 4
+    b = torch.randn(rows, cols, device="cuda", generator=g) * 4
+    if not get_softmax:
+        a, b = torch.softmax(a, -1), torch.softmax(b, -1)
+    p1, q1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    p2, q2 = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    l1 = js_div(p1, q1, get_softmax)
+    l2 = O.js_div(p2, q2, get_softmax)
+    (-0.7 * l1).backward()
+    (-0.7 * l2).backward()
+    assert abs(l1.item() - l2.item()) <= 2e-5 * max(1.0, abs(l2.item()))
+    for got, ref in ((p1.grad, p2.grad), (q1.grad, q2.grad)):
+        assert (got.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-9
+    with pytest.raises(RuntimeError):
+        js_div(a.cpu(), b.cpu())

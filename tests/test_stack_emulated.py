@@ -237,3 +237,23 @@ def test_emulated_layer_hooks_deliver_every_live_gradient(emulated):
         assert p.grad is not None, name
         assert torch.equal(v, p.grad), name
     red.uninstall()
+
+
+@pytest.mark.parametrize("get_softmax", [True, False])
+def test_emulated_js_div_matches_reference_formula(emulated, get_softmax):
+    """XModules.js_div mirror (autograd node over the fused kernel's arithmetic) == the reference formula with
+    torch autograd (oracle restatement of XModules.py:32-41), value and both gradients."""
+    from d2r_b200.interaction.XModules import js_div
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(7, 7, generator=g) * 3
+    b = torch.randn(7, 7, generator=g) * 3
+    if not get_softmax:
+        a, b = torch.softmax(a, -1), torch.softmax(b, -1)
+    p1, q1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    p2, q2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    l1 = js_div(p1, q1, get_softmax)
+    l2 = O.js_div(p2, q2, get_softmax)
+    (3.0 * l1).backward()
+    (3.0 * l2).backward()
+    assert abs(l1.item() - l2.item()) <= 1e-6 * max(1.0, abs(l2.item()))
+    assert relerr(p1.grad, p2.grad) < 1e-5 and relerr(q1.grad, q2.grad) < 1e-5
