@@ -110,6 +110,8 @@ SYMBOLS = {
     "d2r_gate_fuse_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "d2r_js_div_fwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "d2r_js_div_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "d2r_block_merge_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "d2r_block_merge_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
 }
 
 

@@ -470,6 +470,85 @@ __global__ void __launch_bounds__(kThreads) js_div_bwd_kernel(const float* __res
     dq[row * cols + c] = up * (get_softmax ? Q * (gq - dotq) : gq);
   }
 }
+
+// ------------------------------------------------------------------ Block fusion core: one warp per (sample, chunk)
+// XModules.py:538-543.  Lanes own the chunk positions s = lane + 32 i (S <= 128).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) block_merge_fwd_kernel(const T* __restrict__ m0, const T* __restrict__ m1,
+                                                                   long long units, int R, int S, T* __restrict__ z,
+                                                                   float* __restrict__ r, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const long long u = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);   // = b * C + c
+  if (u >= units) return;
+  const T* a = m0 + u * R * S;
+  const T* b = m1 + u * R * S;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < R; ++k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = lane + 32 * i;
+      if (s < S) acc[i] = fmaf(Elem<T>::ld(a + k * S + s), Elem<T>::ld(b + k * S + s), acc[i]);
+    }
+  }
+  float zs[4], n2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    zs[i] = copysignf(sqrtf(fabsf(acc[i])), acc[i]);
+    if (lane + 32 * i < S) n2 = fmaf(zs[i], zs[i], n2);
+  }
+  n2 = warp_sum(n2);
+  const float inv = 1.f / fmaxf(sqrtf(n2), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int s = lane + 32 * i;
+    if (s < S) {
+      Elem<T>::st(z + u * S + s, zs[i] * inv);
+      r[u * S + s] = acc[i];
+    }
+  }
+  if (lane == 0) inv_norm[u] = inv;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) block_merge_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ m0,
+                                                                   const T* __restrict__ m1, const float* __restrict__ r,
+                                                                   const float* __restrict__ inv_norm, long long units,
+                                                                   int R, int S, T* __restrict__ dm0,
+                                                                   T* __restrict__ dm1) {
+  const int lane = threadIdx.x & 31;
+  const long long u = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (u >= units) return;
+  const float inv = inv_norm[u];
+  float rv[4], zn[4], g[4], dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int s = lane + 32 * i;
+    rv[i] = s < S ? r[u * S + s] : 0.f;
+    g[i] = s < S ? Elem<T>::ld(dz + u * S + s) : 0.f;
+    zn[i] = copysignf(sqrtf(fabsf(rv[i])), rv[i]) * inv;
+    dot = fmaf(zn[i], g[i], dot);
+  }
+  dot = warp_sum(dot);
+  float dr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float dzs = (g[i] - zn[i] * dot) * inv;               // through z = zs / ||zs||
+    const float sq = sqrtf(fabsf(rv[i]));
+    dr[i] = sq > 0.f ? dzs * 0.5f / sq : 0.f;                    // through zs = sign(r) sqrt|r|
+  }
+  const T* a = m0 + u * R * S;
+  const T* b = m1 + u * R * S;
+  for (int k = 0; k < R; ++k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = lane + 32 * i;
+      if (s < S) {
+        Elem<T>::st(dm0 + u * R * S + k * S + s, dr[i] * Elem<T>::ld(b + k * S + s));
+        Elem<T>::st(dm1 + u * R * S + k * S + s, dr[i] * Elem<T>::ld(a + k * S + s));
+      }
+    }
+  }
+}
 }  // namespace
 
 // ======================================================================== C ABI
@@ -682,6 +761,36 @@ int d2r_js_div_bwd(const float* p, const float* q, int64_t rows, int32_t cols, i
   js_div_bwd_kernel<<<(unsigned)rows, kThreads, 0, st>>>(p, q, cols, get_softmax, 0.5f / (float)rows, d_loss, dp, dq);
   count_launch();
   return check_launch("js_div_bwd_kernel");
+}
+
+int d2r_block_merge_fwd(const void* m0, const void* m1, int32_t dtype, int64_t B, int32_t C, int32_t R, int32_t S,
+                        void* z, float* r, float* inv_norm, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(m0 && m1 && z && r && inv_norm && C >= 1 && R >= 1 && S >= 1 && S <= 128 && B >= 0,
+                "block_merge_fwd: bad arguments (chunk size must be <= 128)");
+  const long long units = (long long)B * C;
+  if (units == 0) return D2R_OK;
+  const unsigned grid = (unsigned)((units + kThreads / 32 - 1) / (kThreads / 32));
+  D2R_DISPATCH_DTYPE(dtype, T, block_merge_fwd_kernel<T><<<grid, kThreads, 0, st>>>((const T*)m0, (const T*)m1, units,
+                                                                                     R, S, (T*)z, r, inv_norm));
+  count_launch();
+  return check_launch("block_merge_fwd_kernel");
+}
+
+int d2r_block_merge_bwd(const void* dz, const void* m0, const void* m1, const float* r, const float* inv_norm,
+                        int32_t dtype, int64_t B, int32_t C, int32_t R, int32_t S, void* dm0, void* dm1,
+                        void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(dz && m0 && m1 && r && inv_norm && dm0 && dm1 && C >= 1 && R >= 1 && S >= 1 && S <= 128 && B >= 0,
+                "block_merge_bwd: bad arguments (chunk size must be <= 128)");
+  const long long units = (long long)B * C;
+  if (units == 0) return D2R_OK;
+  const unsigned grid = (unsigned)((units + kThreads / 32 - 1) / (kThreads / 32));
+  D2R_DISPATCH_DTYPE(dtype, T, block_merge_bwd_kernel<T><<<grid, kThreads, 0, st>>>(
+                                   (const T*)dz, (const T*)m0, (const T*)m1, r, inv_norm, units, R, S, (T*)dm0,
+                                   (T*)dm1));
+  count_launch();
+  return check_launch("block_merge_bwd_kernel");
 }
 
 }  // extern "C"

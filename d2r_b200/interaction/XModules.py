@@ -129,3 +129,46 @@ class AttentionFiltration(nn.Module):
             return (torch.cat([d_sg.unsqueeze(1), d_sl], 1),)
 
         return run_block(self, [sim_emb], fwd, bwd)[0]
+
+
+class Block(nn.Module):
+    """Mirror of reference models/XModules.py:478-555 (bilinear fusion of the two pooled branch outputs,
+    ``modeling_unimo.py:776,884``): same constructor signature, parameter names / shapes / creation order.
+    The drop-in covers what the reference instantiates -- ``shared=False``, no dropout, ``pos_norm='before_cat'``,
+    ``mm_dim`` divisible by ``chunks`` -- and refuses the other (never used) option values at construction."""
+
+    def __init__(self, input_dims, output_dim, mm_dim=1600, chunks=20, rank=15, shared=False, dropout_input=0.,
+                 dropout_pre_lin=0., dropout_output=0., pos_norm='before_cat'):
+        super(Block, self).__init__()
+        size = mm_dim // chunks
+        if shared or dropout_input or dropout_pre_lin or dropout_output or pos_norm != 'before_cat':
+            raise ValueError("d2r_b200.Block: only shared=False, dropout 0 and pos_norm='before_cat' are supported")
+        if mm_dim % chunks or size % 8 or size > 128:
+            raise ValueError("d2r_b200.Block: mm_dim / chunks must be an integer multiple of 8, at most 128")
+        self.input_dims, self.output_dim, self.mm_dim = input_dims, output_dim, mm_dim
+        self.chunks, self.rank, self.shared = chunks, rank, shared
+        self.dropout_input, self.dropout_pre_lin, self.dropout_output = dropout_input, dropout_pre_lin, dropout_output
+        self.pos_norm = pos_norm
+        self.linear0 = nn.Linear(input_dims[0], mm_dim)
+        self.linear1 = nn.Linear(input_dims[1], mm_dim)
+        self.sizes_list = [size] * chunks
+        merge_linears0, merge_linears1 = [], []
+        for s in self.sizes_list:                      # creation order alternates, as upstream (:507-515)
+            merge_linears0.append(nn.Linear(s, s * rank))
+            merge_linears1.append(nn.Linear(s, s * rank))
+        self.merge_linears0 = nn.ModuleList(merge_linears0)
+        self.merge_linears1 = nn.ModuleList(merge_linears1)
+        self.linear_out = nn.Linear(mm_dim, output_dim)
+        self.n_params = sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def forward(self, x):
+        chunks, rank = self.chunks, self.rank
+
+        def fwd(env, ts):
+            out, st = S.block_forward(env, ts[0], ts[1], chunks, rank)
+            return (out,), st
+
+        def bwd(env, st, grads):
+            return S.block_backward(env, st, grads[0])
+
+        return run_block(self, [x[0], x[1]], fwd, bwd)[0]

@@ -280,6 +280,28 @@ def js_div_bwd(p: Tensor, q: Tensor, d_loss: Tensor, get_softmax: bool = True):
     return dp, dq
 
 
+def block_merge_fwd(m0: Tensor, m1: Tensor, chunks: int, rank: int, size: int):
+    """Block fusion core (XModules.py:538-543): m0, m1 [B, chunks*rank*size] -> z [B, chunks*size] (same dtype),
+    r [B, chunks*size] fp32, inv_norm [B, chunks] fp32."""
+    L.require_cuda(m0, m1)
+    B = m0.shape[0]
+    z = torch.empty(B, chunks * size, device=m0.device, dtype=m0.dtype)
+    r = torch.empty(B, chunks * size, device=m0.device, dtype=torch.float32)
+    inv = torch.empty(B, chunks, device=m0.device, dtype=torch.float32)
+    L.check(L.lib.d2r_block_merge_fwd(m0.data_ptr(), m1.data_ptr(), L.dt(m0), B, chunks, rank, size, z.data_ptr(),
+                                      r.data_ptr(), inv.data_ptr(), L.stream()), "block_merge_fwd")
+    return z, r, inv
+
+
+def block_merge_bwd(dz: Tensor, m0: Tensor, m1: Tensor, r: Tensor, inv: Tensor, chunks: int, rank: int, size: int):
+    B = m0.shape[0]
+    dm0, dm1 = torch.empty_like(m0), torch.empty_like(m1)
+    L.check(L.lib.d2r_block_merge_bwd(dz.data_ptr(), m0.data_ptr(), m1.data_ptr(), r.data_ptr(), inv.data_ptr(),
+                                      L.dt(m0), B, chunks, rank, size, dm0.data_ptr(), dm1.data_ptr(), L.stream()),
+            "block_merge_bwd")
+    return dm0, dm1
+
+
 def router_head_fwd(hid: Tensor, w2: Sequence[Tensor], b2: Sequence[Tensor], n_out: int, final_layer: bool):
     """hid [K,B,H] fp32 (post-ReLU) -> raw, norm [B,n_out,K], gate [B,n_out] ([B,K] in the final layer)."""
     K_, B, H = hid.shape

@@ -708,6 +708,57 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     return d_xs, d_pooled, dz
 
 
+# ----------------------------------------------------------------------------- Block fusion
+def block_forward(env: Env, x0: Tensor, x1: Tensor, chunks: int, rank: int):
+    """XModules.py:521-555: linear0/1 -> chunk-wise merge linears (ONE batched GEMM per side instead of the
+    reference's Python loop over 20 chunks) -> fused rank-sum / signed sqrt / per-chunk L2 norm -> linear_out.
+    x0, x1: [B, D] in env.cd.  Returns (out [B, output_dim] env.cd, state)."""
+    B = x0.shape[0]
+    a = K.linear(x0, env.W("linear0"), env.b("linear0"))
+    b = K.linear(x1, env.W("linear1"), env.b("linear1"))
+    mm = a.shape[1]
+    S = mm // chunks
+    RS = rank * S
+    ms = []
+    for side, src in (("merge_linears0", a), ("merge_linears1", b)):
+        names = [f"{side}.{c}" for c in range(chunks)]
+        m = torch.empty(B, chunks * RS, device=a.device, dtype=env.cd)
+        K.gemm(src, env.W(*names), m, m=B, n=RS, k=S, lda=mm, ldb=S, ldc=chunks * RS, batch=chunks,
+               a_str=(S, 0), b_str=(RS * S, 0), c_str=(RS, 0), bias=env.b(*names), bias_sz=RS)
+        ms.append(m)
+    z, r, inv = K.block_merge_fwd(ms[0], ms[1], chunks, rank, S)
+    out = K.linear(z, env.W("linear_out"), env.b("linear_out"))
+    return out, dict(x0=x0, x1=x1, a=a, b=b, m0=ms[0], m1=ms[1], z=z, r=r, inv=inv, chunks=chunks, rank=rank)
+
+
+def block_backward(env: Env, st, d_out: Tensor):
+    """-> (dx0, dx1) in env.cd; parameter gradients in env.G."""
+    chunks, rank = st["chunks"], st["rank"]
+    a, b, z = st["a"], st["b"], st["z"]
+    B, mm = a.shape
+    S = mm // chunks
+    RS = rank * S
+    d_out = d_out.contiguous() if d_out.dtype == env.cd else K.cast(d_out.contiguous(), env.cd)
+    dz = lin_bwd(env, d_out, z, mm, env.W("linear_out"), ["linear_out"])
+    dms = K.block_merge_bwd(dz, st["m0"], st["m1"], st["r"], st["inv"], chunks, rank, S)
+    dxs = []
+    for side, src, dm, lin, x in (("merge_linears0", a, dms[0], "linear0", st["x0"]),
+                                  ("merge_linears1", b, dms[1], "linear1", st["x1"])):
+        names = [f"{side}.{c}" for c in range(chunks)]
+        _, db = K.bias_act_bwd(dm, None, L.ACT_NONE, False, True)
+        dW = torch.empty(chunks * RS, S, device=dm.device, dtype=torch.float32)
+        K.gemm(dm, src, dW, m=RS, n=S, k=B, lda=chunks * RS, ldb=mm, ldc=S, a_mn=True, b_mn=True, batch=chunks,
+               a_str=(RS, 0), b_str=(S, 0), c_str=(RS * S, 0))
+        for c, nme in enumerate(names):
+            env.grad(nme + ".weight", dW[c * RS:(c + 1) * RS])
+            env.grad(nme + ".bias", db[c * RS:(c + 1) * RS])
+        dsrc = torch.empty(B, mm, device=dm.device, dtype=env.cd)
+        K.gemm(dm, env.W(*names), dsrc, m=B, n=S, k=RS, lda=chunks * RS, ldb=S, ldc=mm, b_mn=True, batch=chunks,
+               a_str=(RS, 0), b_str=(RS * S, 0), c_str=(S, 0))
+        dxs.append(lin_bwd(env, dsrc, x, x.shape[1], env.W(lin), [lin]))
+    return dxs[0], dxs[1]
+
+
 # ----------------------------------------------------------------------------- whole stack
 def layer_prefixes(R: int) -> List[str]:
     return ["dynamic_itr_l0"] + [f"dynamic_itr_l1.{i}" for i in range(R - 2)] + ["dynamic_itr_l2"]

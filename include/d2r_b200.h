@@ -235,6 +235,19 @@ int d2r_js_div_fwd(const float* p, const float* q, int64_t rows, int32_t cols, i
 int d2r_js_div_bwd(const float* p, const float* q, int64_t rows, int32_t cols, int32_t get_softmax,
                    const float* d_loss, float* dp, float* dq, void* stream);
 
+/* Block bilinear fusion core (XModules.py:531-545, pos_norm='before_cat'), applied to the two pooled branch
+ * outputs right after the stack (modeling_unimo.py:871-884).  Per sample b and chunk c (size S, rank R):
+ *   r[b,c,s] = sum_{k<R} m0[b,c,k*S+s] * m1[b,c,k*S+s]
+ *   zs = sign(r) sqrt(|r|);   z[b,c,:] = zs / max(||zs||_2, 1e-12)
+ * m0, m1: [B, C*R*S] (dtype), the outputs of the chunk-wise merge linears (one batched d2r_gemm each);
+ * z: [B, C*S] (dtype; the operand of linear_out); r [B, C*S] and inv_norm [B, C] (fp32) are kept for the
+ * backward, which maps dz [B, C*S] to dm0, dm1 [B, C*R*S].  S <= 128. */
+int d2r_block_merge_fwd(const void* m0, const void* m1, int32_t dtype, int64_t B, int32_t C, int32_t R, int32_t S,
+                        void* z, float* r, float* inv_norm, void* stream);
+int d2r_block_merge_bwd(const void* dz, const void* m0, const void* m1, const float* r, const float* inv_norm,
+                        int32_t dtype, int64_t B, int32_t C, int32_t R, int32_t S, void* dm0, void* dm1,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -440,6 +440,44 @@ def js_div(p_output: torch.Tensor, q_output: torch.Tensor, get_softmax: bool = T
     return (kl(log_mean_output, p_output) + kl(log_mean_output, q_output)) / 2
 
 
+def block_param_spec(input_dims=(768, 768), output_dim=768, mm_dim=1600, chunks=20, rank=15):
+    """Parameter names / shapes of XModules.Block in creation order (XModules.py:501-519, shared=False)."""
+    size = mm_dim // chunks
+    spec = [("linear0.weight", (mm_dim, input_dims[0])), ("linear0.bias", (mm_dim,)),
+            ("linear1.weight", (mm_dim, input_dims[1])), ("linear1.bias", (mm_dim,))]
+    for group in ("merge_linears0", "merge_linears1"):
+        for c in range(chunks):
+            spec += [(f"{group}.{c}.weight", (size * rank, size)), (f"{group}.{c}.bias", (size * rank,))]
+    spec += [("linear_out.weight", (output_dim, mm_dim)), ("linear_out.bias", (output_dim,))]
+    return spec
+
+
+def make_block_params(seed: int, **kw) -> Params:
+    g = torch.Generator().manual_seed(seed)
+    P: Params = {}
+    for name, shape in block_param_spec(**kw):
+        fan_in = shape[-1] if len(shape) > 1 else 64
+        P[name] = torch.randn(shape, generator=g) / math.sqrt(fan_in) * (0.2 if name.endswith(".bias") else 1.0)
+    return P
+
+
+def block_fusion(P: Params, x0: torch.Tensor, x1: torch.Tensor, chunks: int = 20, rank: int = 15) -> torch.Tensor:
+    """XModules.py:521-555 (Block.forward, pos_norm='before_cat', no dropout): bilinear fusion of the two pooled
+    branch outputs (modeling_unimo.py:871-884).  x0, x1: [B, 768] -> [B, 768]."""
+    a = F.linear(x0, P["linear0.weight"], P["linear0.bias"])                # :522
+    b = F.linear(x1, P["linear1.weight"], P["linear1.bias"])                # :523
+    size = a.shape[1] // chunks
+    zs = []
+    for c in range(chunks):                                                 # :531-545
+        m = F.linear(a[:, c * size:(c + 1) * size], P[f"merge_linears0.{c}.weight"], P[f"merge_linears0.{c}.bias"]) * \
+            F.linear(b[:, c * size:(c + 1) * size], P[f"merge_linears1.{c}.weight"], P[f"merge_linears1.{c}.bias"])
+        z = m.view(a.shape[0], rank, -1).sum(1)                             # :539-540
+        z = torch.sqrt(F.relu(z)) - torch.sqrt(F.relu(-z))                  # :542
+        zs.append(F.normalize(z, p=2))                                      # :543
+    z = torch.cat(zs, 1)
+    return F.linear(z, P["linear_out.weight"], P["linear_out.bias"])        # :552
+
+
 def is_zero_grad_param(name: str, training: bool) -> bool:
     """Parameters whose gradient is mathematically zero (softmax shift invariance of a key-projection bias;
     a bias in front of train-mode BatchNorm): both sides only hold rounding noise."""

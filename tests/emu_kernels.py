@@ -182,6 +182,27 @@ def js_div_bwd(p, q, d_loss, get_softmax=True):
     return up * gp, up * gq
 
 
+def block_merge_fwd(m0, m1, chunks, rank, size):
+    B = m0.shape[0]
+    r = (m0.float() * m1.float()).view(B, chunks, rank, size).sum(2)
+    zs = torch.sign(r) * r.abs().sqrt()
+    inv = 1.0 / zs.norm(dim=-1).clamp_min(1e-12)
+    return (zs * inv.unsqueeze(-1)).reshape(B, chunks * size).to(m0.dtype), r.reshape(B, chunks * size), inv
+
+
+def block_merge_bwd(dz, m0, m1, r, inv, chunks, rank, size):
+    B = m0.shape[0]
+    rv = r.view(B, chunks, size)
+    zn = torch.sign(rv) * rv.abs().sqrt() * inv.unsqueeze(-1)
+    g = dz.float().view(B, chunks, size)
+    dzs = (g - zn * (zn * g).sum(-1, keepdim=True)) * inv.unsqueeze(-1)
+    sq = rv.abs().sqrt()
+    dr = torch.where(sq > 0, dzs * 0.5 / sq.clamp_min(1e-30), torch.zeros_like(sq)).unsqueeze(2)
+    dm0 = (dr * m1.float().view(B, chunks, rank, size)).reshape(B, -1).to(m0.dtype)
+    dm1 = (dr * m0.float().view(B, chunks, rank, size)).reshape(B, -1).to(m0.dtype)
+    return dm0, dm1
+
+
 def gate_fuse_bwd(d_out, g, t, i):
     dg = d_out * (t - i)
     return g * (dg - (dg * g).sum(-1, keepdim=True)), d_out * g, d_out * (1 - g)

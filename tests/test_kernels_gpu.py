@@ -287,3 +287,30 @@ def test_js_div_vs_reference_formula(rows, cols, get_softmax):
         assert (got.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-9
     with pytest.raises(RuntimeError):
         js_div(a.cpu(), b.cpu())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_block_merge_kernels(dtype):
+    """Rank-sum / signed sqrt / per-chunk L2 norm of XModules.Block (:538-543) and its backward against a torch fp64
+    restatement.  m1 = m0 * positive factors keeps r = sum_k m0 m1 away from zero, where the map is well
+    conditioned (its derivative 1 / (2 sqrt|r|) is unbounded at 0)."""
+    from d2r_b200 import kernels as K
+    B, C, R, S = 9, 20, 15, 80
+    g = torch.Generator(device="cuda").manual_seed(3)
+    m0 = torch.randn(B, C * R * S, device="cuda", generator=g).to(dtype)
+    m1 = (m0.float() * (0.5 + torch.rand(B, C * R * S, device="cuda", generator=g))).to(dtype)
+    sign = torch.where(torch.rand(B, C, 1, 1, device="cuda", generator=g) < 0.5, -1.0, 1.0)   # negative r too
+    m1 = (m1.float().view(B, C, R, S) * sign).reshape(B, -1).to(dtype)
+    a, b = m0.double().requires_grad_(True), m1.double().requires_grad_(True)
+    r_ref = (a * b).view(B, C, R, S).sum(2)
+    zs = torch.sqrt(torch.relu(r_ref)) - torch.sqrt(torch.relu(-r_ref))
+    z_ref = torch.nn.functional.normalize(zs, p=2, dim=-1).reshape(B, C * S)
+    dz = torch.randn(B, C * S, device="cuda", generator=g).to(dtype)
+    (z_ref * dz.double()).sum().backward()
+    z, r, inv = K.block_merge_fwd(m0, m1, C, R, S)
+    dm0, dm1 = K.block_merge_bwd(dz, m0, m1, r, inv, C, R, S)
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert (z.double() - z_ref).abs().max().item() <= tol
+    assert (r.double() - r_ref.reshape(B, -1)).abs().max().item() <= 1e-4 * r_ref.abs().max().item()
+    for got, ref in ((dm0, a.grad), (dm1, b.grad)):
+        assert (got.double() - ref).abs().max().item() <= tol * ref.abs().max().item() + 1e-7

@@ -257,3 +257,30 @@ def test_emulated_js_div_matches_reference_formula(emulated, get_softmax):
     (3.0 * l2).backward()
     assert abs(l1.item() - l2.item()) <= 1e-6 * max(1.0, abs(l2.item()))
     assert relerr(p1.grad, p2.grad) < 1e-5 and relerr(q1.grad, q2.grad) < 1e-5
+
+
+def test_emulated_block_fusion_matches_reference_golden(emulated):
+    """XModules.Block mirror vs the fixture generated by the unmodified reference class
+    (tests/golden/make_block_golden.py): output, input gradients, every parameter gradient digest, and the
+    seeded default initialisation."""
+    from d2r_b200.interaction.XModules import Block
+    from tests.golden.make_block_golden import BLOCK_PARAM_SEED, block_inputs
+    gold = np.load(os.path.join(GOLD, "block_fusion.npz"))
+    torch.manual_seed(2023)
+    m = Block([768, 768], 768)
+    assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == O.block_param_spec()
+    np.testing.assert_allclose([float(p.detach().double().sum()) for p in m.parameters()], gold["init_sum"],
+                               rtol=0, atol=1e-9)
+    m.load_state_dict(O.make_block_params(BLOCK_PARAM_SEED))
+    x0, x1 = block_inputs()
+    x0.requires_grad_(True)
+    x1.requires_grad_(True)
+    out = m([x0, x1])
+    (out * torch.from_numpy(gold["w"])).sum().backward()
+    assert relerr(out, gold["out"]) < 1e-5
+    assert relerr(x0.grad, gold["d_x0"]) < 1e-4 and relerr(x1.grad, gold["d_x1"]) < 1e-4
+    for n, p in m.named_parameters():
+        got, ref = digest(p.grad), gold["gd/" + n]
+        assert np.abs(got - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), n
+    with pytest.raises(ValueError):
+        Block([768, 768], 768, shared=True)
