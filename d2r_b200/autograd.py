@@ -86,10 +86,8 @@ class _BlocksFn(torch.autograd.Function):
     while its own stream is current, every fork waits on the caller's stream and every call joins before it
     returns, so no block of memory is reused across lanes without an ordering edge."""
 
-    last_out_counts: List[int] = []
-
     @staticmethod
-    def forward(ctx, specs, *tensors):
+    def forward(ctx, specs, out_counts, *tensors):
         dev = next(t.device for t in tensors if t is not None)
         lanes, first = _block_lanes(dev, len(specs))
         recs, all_outs, off = [], [], 0
@@ -103,7 +101,7 @@ class _BlocksFn(torch.autograd.Function):
         lanes.join()
         ctx.recs = recs
         ctx.dev = dev
-        _BlocksFn.last_out_counts = [len(o) for o in all_outs]
+        out_counts.extend(len(o) for o in all_outs)     # (caller-owned list: how to split the flat result)
         nd = [outs[j] for outs, spec in zip(all_outs, specs) for j in spec[9]]
         if nd:
             ctx.mark_non_differentiable(*nd)
@@ -113,7 +111,7 @@ class _BlocksFn(torch.autograd.Function):
     def backward(ctx, *grads):
         recs = ctx.recs
         lanes, first = _block_lanes(ctx.dev, len(recs))
-        res: List[Optional[Tensor]] = [None]
+        res: List[Optional[Tensor]] = [None, None]
         off = 0
         for i, rec in enumerate(recs):
             n = len(rec["out_meta"])
@@ -161,7 +159,7 @@ def run_block(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]],
     """See module docstring.  ``prefix`` is prepended to the module's parameter names so that helper
     code written against full stack names (e.g. 'L.glac.fc_1') can serve a stand-alone sub-module."""
     spec, tensors = _make_spec(module, inputs, fwd, bwd, prefix=prefix, cd=cd, heads=heads, out_nondiff=out_nondiff)
-    return _BlocksFn.apply((spec,), *tensors)
+    return _BlocksFn.apply((spec,), [], *tensors)
 
 
 def run_blocks(requests: Sequence[dict]) -> List[Tuple[Tensor, ...]]:
@@ -173,10 +171,11 @@ def run_blocks(requests: Sequence[dict]) -> List[Tuple[Tensor, ...]]:
         spec, ts = _make_spec(rq.pop("module"), rq.pop("inputs"), rq.pop("fwd"), rq.pop("bwd"), **rq)
         specs.append(spec)
         tensors += ts
-    flat = _BlocksFn.apply(tuple(specs), *tensors)
+    counts: List[int] = []
+    flat = _BlocksFn.apply(tuple(specs), counts, *tensors)
     # split by each block's number of outputs: not known before the forward ran, so the forward reports it
     res, off = [], 0
-    for n in _BlocksFn.last_out_counts:
+    for n in counts:
         res.append(tuple(flat[off:off + n]))
         off += n
     return res
