@@ -44,12 +44,14 @@ class Stager:
     """Per-module cache of GEMM-ready weights: bf16 copies (bf16 mode) and row-concatenated weights
     that share an A operand (QKV, the K/V projections of all cross-modal cells, FiLM scale|shift).
     Entries are refreshed when a parameter's version counter or storage changes; inside a CUDA-graph
-    capture they are always refreshed so that the cast kernels are part of the graph."""
+    capture they are refreshed once per stack call (``fresh``: the keys already re-staged by this call's Env), so
+    that the cast kernels are part of the graph but the backward does not repeat the forward's casts."""
 
     def __init__(self):
         self._cache: Dict[tuple, tuple] = {}
 
-    def get(self, names: Tuple[str, ...], params: Dict[str, Tensor], cd: torch.dtype, suffix: str) -> Tensor:
+    def get(self, names: Tuple[str, ...], params: Dict[str, Tensor], cd: torch.dtype, suffix: str,
+            fresh: Optional[set] = None) -> Tensor:
         ps = [params[n + suffix] for n in names]
         if len(ps) == 1 and ps[0].dtype == cd:
             return ps[0].detach()
@@ -57,7 +59,7 @@ class Stager:
         sig = tuple((p.data_ptr(), p._version) for p in ps)
         hit = self._cache.get(key)
         capturing = ps[0].is_cuda and torch.cuda.is_current_stream_capturing()
-        if hit is not None and hit[0] == sig and not capturing:
+        if hit is not None and hit[0] == sig and (not capturing or (fresh is not None and key in fresh)):
             return hit[1]
         rows = sum(p.shape[0] for p in ps)
         shape = (rows,) + tuple(ps[0].shape[1:])
@@ -68,6 +70,8 @@ class Stager:
             K.cast(p.detach(), cd, out=buf[r:r + p.shape[0]])
             r += p.shape[0]
         self._cache[key] = (sig, buf)
+        if fresh is not None:
+            fresh.add(key)
         return buf
 
 
@@ -82,11 +86,12 @@ class Env:
         self.training = training
         self.st = stager
         self.layer_hook = None         # callable(layer prefix, {name: grad}) after each layer's backward
+        self._fresh: set = set()       # staged-weight keys this call has already refreshed (see Stager)
         self.heads = heads
         self.G: Dict[str, Tensor] = {}
 
     def W(self, *names: str) -> Tensor:
-        return self.st.get(tuple(names), self.P, self.cd, ".weight")
+        return self.st.get(tuple(names), self.P, self.cd, ".weight", self._fresh)
 
     def Wf32(self, name: str) -> Tensor:
         return self.P[name + ".weight"].detach()
@@ -94,7 +99,7 @@ class Env:
     def b(self, *names: str) -> Tensor:
         if len(names) == 1:
             return self.P[names[0] + ".bias"].detach()
-        return self.st.get(tuple(names), self.P, torch.float32, ".bias")
+        return self.st.get(tuple(names), self.P, torch.float32, ".bias", self._fresh)
 
     def grad(self, name: str, g: Tensor) -> None:
         self.G[name] = g if name not in self.G else self.G[name] + g
