@@ -202,6 +202,8 @@ def own_arm(args):
         LN.CELL_LANES = max(1, args.cell_lanes)
     if args.priority:
         LN.PRIORITIZE_FIRST_BLOCK = True
+    if args.no_aux_bias:
+        LN.AUX_BIAS = False
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -512,6 +514,8 @@ def main():
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="layer-wise gradient all-reduces launched from inside the backward (GradAllReducer.install) "
                          "instead of one collective after it; measured equal at 2 GPUs in round 1, not the default")
+    ap.add_argument("--no-aux-bias", action="store_true",
+                    help="bias-gradient column sums on the GEMMs' own stream instead of a helper stream")
     ap.add_argument("--priority", action="store_true",
                     help="run_pair with high stream priority for the first (text) stack")
     ap.add_argument("--batch-per-gpu", type=int, default=None,

@@ -61,6 +61,7 @@ def _bwd_one(rec, grads) -> List[Optional[Tensor]]:
     for g, (shape, dtype) in zip(grads, rec["out_meta"]):
         gs.append(None if g is None else g.to(dtype).contiguous())
     in_grads = bwd(env, rec["state"], gs)
+    env.aux_sync()                      # helper streams of this pass (bias-gradient sums) rejoin their parents
     rec["state"] = None
     res: List[Optional[Tensor]] = []
     for g, dt in zip(in_grads, rec["in_dtypes"]):

@@ -102,11 +102,25 @@ class NoLanes:
         pass
 
 
+_AUX: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+
+
+def aux_stream(parent) -> "torch.cuda.Stream":
+    """Cached helper stream of ``parent`` for small side computations (bias-gradient column sums) that nothing
+    on the parent's chain waits for."""
+    key = (parent.device.index, parent.cuda_stream)
+    st = _AUX.get(key)
+    if st is None:
+        st = _AUX[key] = torch.cuda.Stream(device=parent.device, priority=parent.priority)
+    return st
+
+
 # Concurrency switches (read at every call): ENABLED=False puts every launch on the caller's stream.
 ENABLED = True
 CELL_LANES = 5      # lanes per routing layer: [K/V + GLAC local | IMRC | CMRC | CRCMC | routers + GESC + GLAC global]
 PRIORITIZE_FIRST_BLOCK = False  # run_pair: high stream priority for the first (text, heavier) stack -- measured
                                 # neutral (23.2 vs 23.1 ms), off
+AUX_BIAS = True     # bias-gradient column sums on a helper stream beside the wgrad / dgrad GEMMs
 FWD_LANES = True    # (bring-up switches: cell lanes in the forward / backward pass)
 BWD_LANES = True
 

@@ -21,6 +21,7 @@ accumulation, fp32 softmax/norm/router statistics; torch.float32 -> fp32 CUDA-co
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -87,8 +88,33 @@ class Env:
         self.st = stager
         self.layer_hook = None         # callable(layer prefix, {name: grad}) after each layer's backward
         self._fresh: set = set()       # staged-weight keys this call has already refreshed (see Stager)
+        self._aux: Dict[int, tuple] = {}   # parent stream handle -> (parent, helper stream, tensors kept alive)
         self.heads = heads
         self.G: Dict[str, Tensor] = {}
+
+    @contextlib.contextmanager
+    def aux(self, *keep: Tensor):
+        """Issue the enclosed launches on the current stream's helper stream (after everything queued so far);
+        nothing on the current stream waits for them until aux_sync().  ``keep``: inputs allocated on the current
+        stream that the helper reads -- held until the sync so that their memory is not reused under it."""
+        t0 = keep[0] if keep else None
+        if t0 is None or not t0.is_cuda or not (LN.ENABLED and LN.AUX_BIAS):
+            yield
+            return
+        cur = torch.cuda.current_stream(t0.device)
+        ent = self._aux.get(cur.cuda_stream)
+        if ent is None:
+            ent = self._aux[cur.cuda_stream] = (cur, LN.aux_stream(cur), [])
+        ent[2].extend(keep)
+        ent[1].wait_stream(cur)
+        with torch.cuda.stream(ent[1]):
+            yield
+
+    def aux_sync(self) -> None:
+        """Every stream that used a helper waits for it (call before a lane is joined / a pass returns)."""
+        for cur, st, _keep in self._aux.values():
+            cur.wait_stream(st)
+        self._aux = {}
 
     def W(self, *names: str) -> Tensor:
         return self.st.get(tuple(names), self.P, self.cd, ".weight", self._fresh)
@@ -138,7 +164,13 @@ def lin_bwd(env: Env, dy: Tensor, x: Tensor, ldx: int, W: Tensor, names: Sequenc
     (e.g. row 0 of every sample), in which case residual is read with the same stride."""
     N, Kd = W.shape
     M = dy.numel() // N
-    dz, db = K.bias_act_bwd(dy, y, act, True, True)
+    if act == L.ACT_NONE:
+        # the bias gradient (column sums of dy) feeds nothing on this chain: helper stream, beside the GEMMs
+        dz = dy
+        with env.aux(dy):
+            _, db = K.bias_act_bwd(dy, None, act, False, True)
+    else:
+        dz, db = K.bias_act_bwd(dy, y, act, True, True)
     tc = W.dtype == torch.bfloat16
     dW = torch.empty(N, Kd, device=W.device, dtype=torch.float32)
     K.gemm(dz, x, dW, m=N, n=Kd, k=M, lda=N, ldb=ldx, ldc=Kd, a_mn=True, b_mn=True,
@@ -687,6 +719,7 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
     dx_glac = _glac_local_bwd(env, pre + ".glac", xs[1], kv, 0, st["glac"], d_t2, d_full[0] if shared_input else None)
     if not shared_input and Kc > 4:
         d_xs[5] = torch.empty_like(xs[5]) if final else torch.zeros_like(xs[5])
+    env.aux_sync()
     lanes.join()
     _row0_bwd_apply(glac_rows[0], dx_glac)
     _row0_bwd_apply(glac_rows[1], dz_rows)
@@ -710,6 +743,7 @@ def layer_backward(env: Env, pre: str, st, d_outs: Sequence[Tensor], d_pooled_ne
             _row0_bwd_apply(gesc_rows[1], dz_rows)
     del d_full, d_bvec                               # (kept alive until the join: read by the side lanes)
     dz = kv.backward(env, dz_rows)
+    env.aux_sync()
     return d_xs, d_pooled, dz
 
 
