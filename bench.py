@@ -204,6 +204,8 @@ def own_arm(args):
         LN.PRIORITIZE_FIRST_BLOCK = True
     if args.no_aux_bias:
         LN.AUX_BIAS = False
+    if args.aux_wgrad:
+        LN.AUX_WGRAD = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -514,6 +516,7 @@ def main():
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="layer-wise gradient all-reduces launched from inside the backward (GradAllReducer.install) "
                          "instead of one collective after it; measured equal at 2 GPUs in round 1, not the default")
+    ap.add_argument("--aux-wgrad", action="store_true", help="weight-gradient GEMMs on the helper stream as well")
     ap.add_argument("--no-aux-bias", action="store_true",
                     help="bias-gradient column sums on the GEMMs' own stream instead of a helper stream")
     ap.add_argument("--priority", action="store_true",

@@ -121,6 +121,7 @@ CELL_LANES = 5      # lanes per routing layer: [K/V + GLAC local | IMRC | CMRC |
 PRIORITIZE_FIRST_BLOCK = False  # run_pair: high stream priority for the first (text, heavier) stack -- measured
                                 # neutral (23.2 vs 23.1 ms), off
 AUX_BIAS = True     # bias-gradient column sums on a helper stream beside the wgrad / dgrad GEMMs
+AUX_WGRAD = False    # (experiment) weight-gradient GEMMs on the helper stream as well
 FWD_LANES = True    # (bring-up switches: cell lanes in the forward / backward pass)
 BWD_LANES = True
 

@@ -173,8 +173,9 @@ def lin_bwd(env: Env, dy: Tensor, x: Tensor, ldx: int, W: Tensor, names: Sequenc
         dz, db = K.bias_act_bwd(dy, y, act, True, True)
     tc = W.dtype == torch.bfloat16
     dW = torch.empty(N, Kd, device=W.device, dtype=torch.float32)
-    K.gemm(dz, x, dW, m=N, n=Kd, k=M, lda=N, ldb=ldx, ldc=Kd, a_mn=True, b_mn=True,
-           split_k=_split_k(N, Kd, M, tc))
+    with (env.aux(dz, x) if LN.AUX_WGRAD else contextlib.nullcontext()):
+        K.gemm(dz, x, dW, m=N, n=Kd, k=M, lda=N, ldb=ldx, ldc=Kd, a_mn=True, b_mn=True,
+               split_k=_split_k(N, Kd, M, tc))
     r = 0
     for nme in names:
         rows = env.P[nme + ".weight"].shape[0]
