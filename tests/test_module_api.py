@@ -219,3 +219,16 @@ def test_dp_layerwise_allreduce_gloo_world2():
         assert p.exitcode == 0
     assert res[0][1] == res[1][1]                     # both ranks hold the same averaged bucket
     assert res[0][2] and res[1][2]
+
+
+def test_lanes_degrade_to_one_stream_off_cuda():
+    """lanes.fork on a CPU device (the emulated tests) or with n <= 1 or ENABLED = False yields the no-op object
+    with the full interface."""
+    import d2r_b200.lanes as LN
+    for lanes in (LN.fork(torch.device("cpu"), 5, "cells"), LN.fork(torch.device("cpu"), 1)):
+        assert isinstance(lanes, LN.NoLanes)
+        with lanes.lane(3):
+            pass
+        lanes.catch_up(2)
+        lanes.wait_mark(lanes.mark(4))
+        lanes.join()
