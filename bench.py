@@ -2,21 +2,30 @@
 """Benchmark of the routed interaction stack (BASELINE.json metric: routed-interaction samples/sec,
 forward + backward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]                  # this repo's CUDA stack
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference algorithm on CPU
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  # this repo's CUDA stack, BASELINE configs[1]
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the UNMODIFIED reference on the host cores
+    python bench.py --config deep        # BASELINE configs[3]: R=4, K=6, text 256 + 197 image tokens, fwd+bwd
+    python bench.py --config eval-sweep  # BASELINE configs[4]: eval / no_grad, batch 2 .. 4096 per GPU
 
-Workload (BASELINE.json configs[1]): both branch stacks (text branch + image branch, K=6 cells, R=3 routing
-layers, text 128 + 50 image tokens, hidden 768), bf16 arithmetic with fp32 accumulation, batch 256 per
-GPU, one step = forward + backward of both stacks (loss = out.sum() + sim_paths.sum() per branch,
-SURVEY §8d) + the data-parallel gradient all-reduce when N > 1.  Synthetic N(0,1) inputs, reference
-default-init weights.
+Default workload (BASELINE.json configs[1]): both branch stacks (text branch + image branch, K=6 cells, R=3 routing
+layers, text 128 + 50 image tokens, hidden 768), bf16 arithmetic with fp32 accumulation, batch 256 per GPU, one step
+= forward + backward of both stacks (loss = out.sum() + sim_paths.sum() per branch) + the data-parallel
+gradient all-reduce when N > 1.  Synthetic N(0,1) inputs, reference default-init weights.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step driven from
-pinned HOST buffers through the nn.Module API with the H2D copy of the inputs and a D2H read of the loss
-inside the timed region.  `roofline`: all tcgen05 GEMM launches of a step, algorithmic FLOPs (2*m*n*k per
-problem, no padding) over their CUDA-event durations, against the measured bf16 peak in MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port (oracle/d2r_oracle.py, with the reference's discarded reverse-attention
-branch executed so that it pays the reference's real cost) on this box's host cores, bounded sample.
+One JSON line on stdout (rank 0).
+  value        inputs resident in HBM, CUDA-graph replay, CUDA events, max over ranks
+  e2e          the same step driven from pinned HOST buffers through the nn.Module API, H2D copy of the inputs and a
+               D2H read of the loss inside the timed region
+  roofline     all tensor-core launches of a step (tcgen05 GEMMs + fused attention kernels): algorithmic FLOPs
+               (2*m*n*k per problem, no padding) over their CUDA-event durations, against the measured sustained bf16
+               peak of MEASURED_PEAKS.json
+  roofline_hbm the aggregation kernels (north_star (c)): algorithmic bytes over CUDA-event durations against the
+               measured copy bandwidth
+  cpu_baseline the UNMODIFIED reference modules (baseline/_ref, staged by __graft_entry__.build()) on this box's host
+               cores, fp32, GPU hidden, bounded sample (batch 8); kind "reference".  Falls back to the oracle port
+               (kind "port") only if the staged copy is missing.
+  stock_pytorch_b200   the same unmodified reference modules on this B200 under torch.autocast(bfloat16), same batch,
+               fwd+bwd, CUDA events: the honest "before" 
 """
 from __future__ import annotations
 
@@ -32,15 +41,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LT, LI, D, KC, R = 128, 50, 768, 6, 3
-BATCH_PER_GPU = 256
-# DRAM traffic of the dominant GEMM launch (ncu --set full, profiles/r01_ncu_gemm_k768_pair.txt): the m=32768, n=768,
-# k=768 projection reads 51.6 MB and writes 10.4 MB per launch against 101.8 MB of algorithmic operand bytes (the
-# bf16 output mostly stays in L2): no wasted re-reads.
+D, KC = 768, 6
+CONFIGS = {
+    # name: Lt, Li, R, batch per GPU, train?, BASELINE.json config index, description
+    "stack": dict(Lt=128, Li=50, R=3, B=256, train=True, idx=1,
+                  desc="D2R routed interaction stack, both branches (text+image), bf16 fwd+bwd, K=6 cells, "
+                       "R=3 routing layers, text 128 + 50 image tokens, hidden 768 (BASELINE configs[1])"),
+    "deep": dict(Lt=256, Li=197, R=4, B=256, train=True, idx=3,
+                 desc="deep routing: both branches, bf16 fwd+bwd, K=6 cells, R=4 routing layers, text 256 + 197 image "
+                      "tokens (ViT-B/16 patch count), hidden 768 (BASELINE configs[3])"),
+    "eval-sweep": dict(Lt=128, Li=50, R=3, B=256, train=False, idx=4,
+                       desc="inference-only (eval, no_grad) throughput sweep, both branches, bf16, K=6, R=3, text 128 "
+                            "+ 50 image tokens, batch 2..4096 per GPU (BASELINE configs[4])"),
+}
+SWEEP_BATCHES = (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096)
+# DRAM traffic of the dominant launches from `ncu --set full` captures (see profiles/): per launch, like `achieved`
 GEMM_TRAFFIC_BYTES = 62.0e6
-GEMM_TRAFFIC_NOTE = ("dram__bytes_read+write of one m=32768 n=768 k=768 launch (60% of the GEMM time is this shape "
-                     "class); ncu capture of round 1, see profiles/r01_ncu_gemm_k768_pair.txt")
+GEMM_TRAFFIC_NOTE = ("dram__bytes_read+write of one m=32768 n=768 k=768 launch (the K=768 projections are 60% of the "
+                     "GEMM time); 101.8 MB algorithmic operand bytes; profiles/r01_ncu_gemm_k768_pair.txt")
 AGG_TRAFFIC_BYTES = 461.3e6
+AGG_TRAFFIC_NOTE = ("agg_fwd_kernel text non-final launch: 503.3 MB algorithmic, 461.3 MB dram "
+                    "(profiles/r01_ncu_agg_fwd.txt)")
 CPU_SAMPLE_BATCH = 8
 
 
@@ -50,7 +71,7 @@ def make_args():
                               bert_name="bert-base-uncased", vit_name="clip-vit-base-patch32")
 
 
-def useful_flops_per_sample(Lt=LT, Li=LI, layers=R):
+def useful_flops_per_sample(Lt, Li, layers):
     """useful forward FLOPs per sample for both branches (dead branch excluded); bwd = 2x fwd."""
     def layer(Lq, Lc):
         lin = lambda L_: 2 * L_ * D * D
@@ -62,24 +83,52 @@ def useful_flops_per_sample(Lt=LT, Li=LI, layers=R):
         gesc = 8 * D * D
         router = 6 * (2 * D * 768 + 2 * 768 * KC + Lq * D)
         agg = 2 * KC * KC * Lq * D
-        return cma * 0 + imrc + glac + cmrc + crcmc + gesc + router + agg
+        return imrc + glac + cmrc + crcmc + gesc + router + agg
     return layers * (layer(Lt, Li) + layer(Li, Lt))
 
 
-# ----------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step_fn(batch, threads=None):
-    """One fwd+bwd of both branch stacks with the oracle port (reference algorithm incl. its dead branch)."""
+def workload_config(name, n_gpus, batch):
+    c = CONFIGS[name]
+    return {"workload": c["desc"], "batch_per_gpu": batch, "global_batch": batch * n_gpus, "text_len": c["Lt"],
+            "image_tokens": c["Li"], "hidden": D, "cells": KC, "routing_layers": c["R"], "parallelism": f"dp{n_gpus}",
+            "l2": "no explicit flush: the per-step working set (several GB of activations) is far larger than the "
+                  "126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------- CPU arms
+def run_reference_subprocess(device, batch, steps, warmup, cfg, bf16=False, timeout=900):
+    """baseline/run_reference.py in a subprocess (GPU hidden for the CPU arm) -> its JSON line (dict) or raises."""
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), "--device", device, "--batch", str(batch),
+           "--steps", str(steps), "--warmup", str(warmup), "--layers", str(cfg["R"]), "--text-len", str(cfg["Lt"]),
+           "--image-tokens", str(cfg["Li"])]
+    if bf16:
+        cmd.append("--bf16")
+    if not cfg["train"]:
+        cmd.append("--eval")
+    env = dict(os.environ)
+    if device == "cpu":
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if out.returncode != 0:
+        raise RuntimeError(f"run_reference.py rc={out.returncode}: {out.stderr.strip().splitlines()[-1:]}")
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def oracle_port_step_fn(batch, cfg, threads=None):
+    """Fallback CPU arm when baseline/_ref is not staged: the oracle port (reference algorithm incl. its dead branch)."""
     import torch
     from oracle import d2r_oracle as O
     if threads:
         torch.set_num_threads(threads)
-    Pt = O.make_params(2023, R, KC)
-    Pi = O.make_params(2024, R, KC)
+    R = cfg["R"]
+    Pt, Pi = O.make_params(2023, R, KC), O.make_params(2024, R, KC)
     for P in (Pt, Pi):
         for k, v in P.items():
             if v.is_floating_point() and "running" not in k and not O.is_dead_param(k):
                 v.requires_grad_(True)
-    text, image = O.make_inputs(2023, batch, LT, LI)
+    text, image = O.make_inputs(2023, batch, cfg["Lt"], cfg["Li"])
     text.requires_grad_(True)
     image.requires_grad_(True)
 
@@ -97,53 +146,54 @@ def cpu_reference_step_fn(batch, threads=None):
     return step
 
 
-def run_cpu_reference(steps, warmup, batch=CPU_SAMPLE_BATCH):
-    import torch
+def cpu_baseline(cfg, steps, warmup):
+    """-> cpu_baseline dict.  Unmodified reference (kind "reference") when staged, else the oracle port."""
+    from baseline import ref_loader as RL
     cores = os.cpu_count() or 1
-    step = cpu_reference_step_fn(batch, cores)
+    what = "fwd+bwd" if cfg["train"] else "eval/no_grad forward"
+    if RL.available():
+        try:
+            r = run_reference_subprocess("cpu", CPU_SAMPLE_BATCH, steps, warmup, cfg)
+            return {"value": r["samples_per_s_mean"], "unit": "samples/s", "cores": r["cores"], "threads": r["threads"],
+                    "kind": "reference", "ms_per_step": 1e3 * r["mean_s_per_step"],
+                    "sample": f"{steps} timed steps of batch {CPU_SAMPLE_BATCH} ({what} of both UNMODIFIED reference "
+                              f"stacks, fp32, torch {r['torch']} CPU, GPU hidden), {warmup} warm-up; "
+                              f"median {r['samples_per_s']:.2f} samples/s"}
+        except Exception as e:      # fall through to the port, say why
+            sys.stderr.write(f"[bench] reference CPU arm failed ({e}); timing the oracle port instead\n")
+    step = oracle_port_step_fn(CPU_SAMPLE_BATCH, cfg, cores)
     for _ in range(warmup):
         step()
-    ts = []
+    t0 = time.perf_counter()
     for _ in range(steps):
-        t0 = time.perf_counter()
         step()
-        ts.append(time.perf_counter() - t0)
-    total = sum(ts)
-    return dict(value=batch * steps / total, ms_per_step=1e3 * total / steps, cores=cores, threads=torch.get_num_threads(),
-                sample=f"{steps} timed steps of batch {batch} (both branch stacks fwd+bwd, fp32, torch CPU, "
-                       f"dead reverse-attention branch executed), {warmup} warm-up")
+    dt = time.perf_counter() - t0
+    return {"value": CPU_SAMPLE_BATCH * steps / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "ms_per_step": 1e3 * dt / steps,
+            "sample": f"{steps} timed steps of batch {CPU_SAMPLE_BATCH} (oracle port of both stacks, fwd+bwd, fp32, "
+                      f"dead reverse-attention branch executed), {warmup} warm-up; baseline/_ref not staged"}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    os.environ["CUDA_VISIBLE_DEVICES"] = ""
-    steps = max(1, args.steps)
-    # bound the run: each step is ~B=8 samples; never more than ~3 minutes of CPU work
-    r = run_cpu_reference(min(steps, 40), min(args.warmup, 3))
+    cfg = CONFIGS[args.config]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # each step is a bounded sample (batch 8) of the workload: ~1-2 s of host time per step
+    r = cpu_baseline(cfg, steps, warmup)
     line = {
         "impl": "reference", "metric": "routed-interaction samples/sec fwd+bwd", "value": r["value"],
-        "unit": "samples/s", "n_gpus": args.gpus, "steps": min(steps, 40), "warmup": min(args.warmup, 3),
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus) | {"cpu_sample_batch": CPU_SAMPLE_BATCH},
-        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                         "sample": r["sample"]},
+        "config": workload_config(args.config, args.gpus, cfg["B"]),
+        "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
-
-
-def workload_config(n_gpus):
-    return {"workload": "D2R routed interaction stack, both branches (text+image), bf16 fwd+bwd, K=6 cells, "
-                        "R=3 routing layers, text 128 + 50 image tokens, hidden 768 (BASELINE configs[1])",
-            "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus, "text_len": LT, "image_tokens": LI,
-            "hidden": D, "cells": KC, "routing_layers": R, "parallelism": f"dp{n_gpus}",
-            "l2": "no explicit flush: the per-step working set (several GB of activations) is far larger "
-                  "than the 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------------- clocks sampler
@@ -206,6 +256,8 @@ def own_arm(args):
         LN.AUX_BIAS = False
     if args.aux_wgrad:
         LN.AUX_WGRAD = True
+    cfg = CONFIGS[args.config]
+    LT, LI, R = cfg["Lt"], cfg["Li"], cfg["R"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,12 +265,14 @@ def own_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = BATCH_PER_GPU
+    B = args.batch_per_gpu or cfg["B"]
 
     torch.manual_seed(2023)
     a = make_args()
-    mt = InteractionModule(a, R, KC, 128).to(dev).train()
-    mi = Reversed_InteractionModule(a, R, KC, 128).to(dev).train()
+    mt = InteractionModule(a, R, KC, 128).to(dev).train(cfg["train"])
+    mi = Reversed_InteractionModule(a, R, KC, 128).to(dev).train(cfg["train"])
+    if args.config == "eval-sweep":
+        return eval_sweep(args, cfg, mt, mi, dev, rank, world, local)
     reducer = GradAllReducer([mt, mi])
 
     g = torch.Generator().manual_seed(2023 + rank)
@@ -309,7 +363,6 @@ def own_arm(args):
     def timed(from_host, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = K.L.launch_count()
         e0.record()
         # `ncu --profile-from-start off` captures exactly the HBM-resident timed region (all threads: the
         # backward kernels are launched from autograd's worker thread, so an NVTX range would miss them)
@@ -326,19 +379,18 @@ def own_arm(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = K.L.launch_count() - n0
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, launches
+        return ms
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # samples cover warm-up + the timed region (both under full load)
     for _ in range(max(args.warmup, 3)):
         step(False)
-    ms, launches = timed(False, args.steps)
+    ms = timed(False, args.steps)
     if ms < 1500.0:
         # keep the GPUs under the same load a little longer so that nvidia-smi (100 ms period) sees it; `ms` is the
         # max over ranks, so every rank runs the same number of extra steps (they contain a collective)
@@ -349,59 +401,52 @@ def own_arm(args):
     prefetch.fetch([h_text, h_image])
     step(True, more=True)
     step(True)
-    ms_e2e, _ = timed(True, args.steps)
-    eager_launches_per_step = None
-    if graph is not None:
-        # kernels launched from a replayed graph do not pass through the C ABI: count one eager step
-        n0 = K.L.launch_count()
-        fwd_bwd(reduce=False)
-        torch.cuda.synchronize()
-        eager_launches_per_step = K.L.launch_count() - n0
-        launches = eager_launches_per_step * args.steps
+    ms_e2e = timed(True, args.steps)
+    # kernels launched from a replayed graph do not pass through the C ABI's counter: count one eager step
+    n0 = K.L.launch_count()
+    fwd_bwd(reduce=False)
+    torch.cuda.synchronize()
+    launches_per_step = K.L.launch_count() - n0
 
-    # --- per-kernel roofline pass (separate, eager, CUDA events around every C-ABI GEMM launch) -----
+    # --- per-kernel roofline pass (separate, eager, CUDA events around every tensor-core / aggregation launch) -----
     # (branches back to back here: kernels of concurrent streams would overlap inside each other's event pairs)
     roof, hbm = kernel_roofline(lambda: fwd_bwd(serial=True, reduce=False), K, torch) if rank == 0 else (None, None)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback"
         samples = B * world * args.steps
         value = samples / (ms / 1e3)
-        flops_step = 3 * useful_flops_per_sample() * B
-        cpu = None
-        try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample"], capture_output=True,
-                                 text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
-            cpu = json.loads(out.stdout.strip().splitlines()[-1])
-        except Exception as e:
-            cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"failed: {e}"}
+        flops_step = 3 * useful_flops_per_sample(LT, LI, R) * B
+        graph_used = graph is not None
+        graph = static_loss = None            # release the graph's private pool before the stock-PyTorch run
+        torch.cuda.empty_cache()
+        cpu = cpu_baseline(cfg, steps=5, warmup=1)
+        stock = stock_pytorch_b200(cfg, B)
+        if stock and stock.get("value"):
+            stock["speedup_of_this_repo"] = value / world / stock["value"]      # per GPU vs one B200
         line = {
             "metric": "routed-interaction samples/sec fwd+bwd", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world) | {"cuda_graph": graph is not None,
-                                                  "branch_streams": 1 if args.serial_branches else 2,
-                                                  "cell_lanes": LN.CELL_LANES,
-                                                  "allreduce": "layer-wise, inside the backward" if overlap
-                                                  else "one per step"},
+            "config": workload_config(args.config, world, B),
+            "engine": {"cuda_graph": graph_used, "branch_streams": 1 if args.serial_branches else 2,
+                       "cell_lanes": LN.CELL_LANES,
+                       "allreduce": "layer-wise, inside the backward" if overlap else "one per step"},
             "clocks": clocks,
             "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": (h_text.numel() + h_image.numel()) * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one fwd+bwd step)",
+                "bound": "tensor", "kernel": "tcgen05 kernels of one fwd+bwd step (gemm_tc*_kernel + fused attention)",
                 "achieved": roof["tflops"], "peak": tc_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tc_peak,
-                "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE, "peak_source": peak_src, "launches_per_step": roof["launches"],
-                "kernel_ms_per_step": roof["ms"], "single_stream_step_ms": roof["serial_step_ms"],
+                "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE, "peak_source": peak_src,
+                "launches_per_step": roof["launches"], "kernel_ms_per_step": roof["ms"],
+                "single_stream_step_ms": roof["serial_step_ms"],
                 "kernel_share_of_step": roof["ms"] / roof["serial_step_ms"],
                 "step_algorithmic_tflops": flops_step / (ms / args.steps / 1e3) / 1e12,
                 "step_frac_of_peak": flops_step / (ms / args.steps / 1e3) / 1e12 / tc_peak,
@@ -409,21 +454,145 @@ def own_arm(args):
             "roofline_hbm": {"bound": "hbm", "kernel": "agg_fwd_kernel / agg_bwd_kernel (aggregation epilogue)",
                              "achieved": hbm["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm["gbs"] / hbm_peak,
                              "launches_per_step": hbm["launches"], "kernel_ms_per_step": hbm["ms"],
-                             "traffic": AGG_TRAFFIC_BYTES,
-                             "traffic_note": "agg_fwd_kernel text non-final launch: 503.3 MB algorithmic, 461.3 MB "
-                                             "dram (profiles/r01_ncu_agg_fwd.txt)"},
+                             "traffic": AGG_TRAFFIC_BYTES, "traffic_note": AGG_TRAFFIC_NOTE},
             "cpu_baseline": cpu,
+            "stock_pytorch_b200": stock,
         }
         emit(line)
     if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def stock_pytorch_b200(cfg, batch):
+    """The unmodified reference modules on this B200 (stock PyTorch eager: cuBLAS + aten) under autocast(bf16)."""
+    from baseline import ref_loader as RL
+    if not RL.available():
+        return {"value": None, "unavailable": "baseline/_ref not staged"}
+    try:
+        r = run_reference_subprocess("cuda", batch, 5, 2, cfg, bf16=True, timeout=600)
+        return {"value": r["samples_per_s"], "unit": "samples/s", "ms_per_step": 1e3 * r["median_s_per_step"],
+                "batch": batch, "dtype": "torch.autocast(bfloat16)", "impl": r["impl"], "torch": r["torch"],
+                "peak_mem_gb": r["peak_mem_gb"],
+                "note": "UNMODIFIED reference InteractionModule + Reversed_InteractionModule, eager PyTorch on the same "
+                        "GPU, same shapes, median of 5 steps after 2 warm-up, CUDA events around forward+backward+"
+                        "loss read"}
+    except Exception as e:
+        return {"value": None, "unavailable": f"{type(e).__name__}: {e}"}
+
+
+def eval_sweep(args, cfg, mt, mi, dev, rank, world, local):
+    """BASELINE configs[4]: eval / no_grad forward of both stacks, batch 2..4096 per GPU, each replayed from its own
+    CUDA graph.  `value` = the best whole-job samples/s of the sweep; every point is in `sweep`."""
+    import torch
+    import torch.distributed as dist
+    from d2r_b200 import kernels as K
+    from d2r_b200.interaction import run_pair
+    LT, LI, R = cfg["Lt"], cfg["Li"], cfg["R"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    points = []
+    h_out = torch.empty(1).pin_memory()
+    for B in SWEEP_BATCHES:
+        try:
+            g = torch.Generator().manual_seed(2023 + rank)
+            h_text = torch.randn(B, LT, D, generator=g).pin_memory()
+            h_image = torch.randn(B, LI, D, generator=g).pin_memory()
+            d_text, d_image = h_text.to(dev), h_image.to(dev)
+
+            def fwd():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    (o1, s1), (o2, s2) = run_pair(mt, mi, d_text, d_image)
+                return o1[0].sum() + o2[0].sum()
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fwd()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = K.L.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                res = fwd()
+            launches = K.L.launch_count() - n0
+            for _ in range(max(args.warmup, 3)):
+                graph.replay()
+
+            def timed(from_host):
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    if from_host:
+                        d_text.copy_(h_text, non_blocking=True)
+                        d_image.copy_(h_image, non_blocking=True)
+                    graph.replay()
+                    if from_host:
+                        h_out.copy_(res.detach().reshape(1), non_blocking=True)
+                        torch.cuda.current_stream().synchronize()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                return ms
+            ms, ms_h = timed(False), timed(True)
+            points.append({"batch_per_gpu": B, "samples_per_s": B * world * args.steps / (ms / 1e3),
+                           "ms_per_step": ms / args.steps, "e2e_samples_per_s": B * world * args.steps / (ms_h / 1e3),
+                           "gpu_launches_per_step": int(launches)})
+            del graph, res, d_text, d_image
+            torch.cuda.empty_cache()
+        except torch.OutOfMemoryError:
+            points.append({"batch_per_gpu": B, "samples_per_s": None, "note": "out of memory"})
+            torch.cuda.empty_cache()
+            break
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        ok = [p for p in points if p.get("samples_per_s")]
+        best = max(ok, key=lambda p: p["samples_per_s"])
+        peaks = load_peaks()
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        fl = useful_flops_per_sample(LT, LI, R)
+        for p in ok:
+            p["frac_of_tensor_peak"] = p["samples_per_s"] / world * fl / 1e12 / tc_peak
+        cpu = cpu_baseline(cfg, steps=5, warmup=1)
+        line = {"metric": "routed-interaction samples/sec forward (eval, no_grad)", "value": best["samples_per_s"],
+                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args.config, world, best["batch_per_gpu"]), "sweep": points, "clocks": clocks,
+                "e2e": {"value": best["e2e_samples_per_s"], "unit": "samples/s",
+                        "h2d_bytes_per_step": best["batch_per_gpu"] * (LT + LI) * D * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": best["gpu_launches_per_step"] * args.steps,
+                "roofline": {"bound": "tensor", "kernel": "whole forward step (useful FLOPs, SURVEY §8d)",
+                             "achieved": best["samples_per_s"] / world * fl / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                             "frac": best["samples_per_s"] / world * fl / 1e12 / tc_peak, "traffic": None},
+                "cpu_baseline": cpu}
+        emit(line)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
 def kernel_roofline(fwd_bwd, K, torch):
-    """Run two eager steps with CUDA events around each tcgen05 GEMM and each aggregation launch."""
+    """Run two eager steps with CUDA events around each tensor-core launch and each aggregation launch."""
     recs = {"gemm": [], "agg": []}
-    orig_gemm, orig_af, orig_ab = K.gemm, K.aggregate_fwd, K.aggregate_bwd
+    orig = {n: getattr(K, n) for n in ("gemm", "aggregate_fwd", "aggregate_bwd")}
+    fused = {n: getattr(K, n) for n in ("attn_fused_fwd", "attn_fused_bwd") if hasattr(K, n)}
 
     def timed_call(kind, work, fn, *a, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -435,27 +604,34 @@ def kernel_roofline(fwd_bwd, K, torch):
 
     def gemm(a, b, c, **kw):
         if a.dtype != torch.bfloat16:
-            return orig_gemm(a, b, c, **kw)
-        return timed_call("gemm", 2.0 * kw["m"] * kw["n"] * kw["k"] * kw.get("batch", 1), orig_gemm, a, b, c, **kw)
+            return orig["gemm"](a, b, c, **kw)
+        return timed_call("gemm", 2.0 * kw["m"] * kw["n"] * kw["k"] * kw.get("batch", 1), orig["gemm"], a, b, c, **kw)
 
     def agg_f(full, bvec, P, gate, final, inputs=None, want_pooled=True):
         x0 = full[0]
         nfull = sum(f is not None for f in full)
         n_out = 1 if final else len(full)
         byts = (nfull + n_out) * x0.numel() * x0.element_size()
-        return timed_call("agg", byts, orig_af, full, bvec, P, gate, final, inputs, want_pooled)
+        return timed_call("agg", byts, orig["aggregate_fwd"], full, bvec, P, gate, final, inputs, want_pooled)
 
     def agg_b(full, bvec, P, gate, final, d_outs, d_pooled, inputs=None):
         x0 = full[0]
         nfull = sum(f is not None for f in full)
         n_out = 1 if final else len(full)
         byts = (n_out + 2 * nfull) * x0.numel() * x0.element_size()
-        return timed_call("agg", byts, orig_ab, full, bvec, P, gate, final, d_outs, d_pooled, inputs)
+        return timed_call("agg", byts, orig["aggregate_bwd"], full, bvec, P, gate, final, d_outs, d_pooled, inputs)
+
+    def fused_wrap(fn):
+        def w(*a, **kw):
+            return timed_call("gemm", kw["flops"], fn, *a, **kw)
+        return w
 
     import d2r_b200.lanes as LN
     lanes_were = LN.ENABLED
     LN.ENABLED = False                  # one stream: concurrent lanes would overlap inside each other's event pairs
     K.gemm, K.aggregate_fwd, K.aggregate_bwd = gemm, agg_f, agg_b
+    for n, fn in fused.items():
+        setattr(K, n, fused_wrap(fn))
     serial_ms = 0.0
     try:
         fwd_bwd()                       # warm
@@ -474,7 +650,9 @@ def kernel_roofline(fwd_bwd, K, torch):
             torch.cuda.synchronize()
             serial_ms += s0.elapsed_time(s1) / nsteps
     finally:
-        K.gemm, K.aggregate_fwd, K.aggregate_bwd = orig_gemm, orig_af, orig_ab
+        K.gemm, K.aggregate_fwd, K.aggregate_bwd = orig["gemm"], orig["aggregate_fwd"], orig["aggregate_bwd"]
+        for n, fn in fused.items():
+            setattr(K, n, fn)
         LN.ENABLED = lanes_were
     gms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["gemm"]) / nsteps
     gfl = sum(w for _, _, w in recs["gemm"]) / nsteps
@@ -511,11 +689,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", default="stack", choices=sorted(CONFIGS),
+                    help="stack = BASELINE configs[1] (the headline); deep = configs[3]; eval-sweep = configs[4]")
     ap.add_argument("--serial-branches", action="store_true",
                     help="call the two branch modules back to back instead of run_pair (two CUDA streams)")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="layer-wise gradient all-reduces launched from inside the backward (GradAllReducer.install) "
-                         "instead of one collective after it; measured equal at 2 GPUs in round 1, not the default")
+                         "instead of one collective after it")
     ap.add_argument("--aux-wgrad", action="store_true", help="weight-gradient GEMMs on the helper stream as well")
     ap.add_argument("--no-aux-bias", action="store_true",
                     help="bias-gradient column sums on the GEMMs' own stream instead of a helper stream")
@@ -526,15 +706,7 @@ def main():
     ap.add_argument("--cell-lanes", type=int, default=None,
                     help="CUDA streams per routing layer (default: d2r_b200.lanes.CELL_LANES; 1 = one stream)")
     ap.add_argument("--no-graph", action="store_true", help="run eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.batch_per_gpu:
-        global BATCH_PER_GPU
-        BATCH_PER_GPU = args.batch_per_gpu
-    if args.cpu_sample:
-        r = run_cpu_reference(steps=4, warmup=1)
-        emit({"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]})
-        return 0
     if args.impl == "reference":
         return reference_arm(args)
     return own_arm(args)

@@ -86,6 +86,7 @@ SYMBOLS = {
     "d2r_last_error": (C.c_char_p, []),
     "d2r_launch_count": (C.c_int64, []),
     "d2r_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "d2r_gemm_set_profile": (C.c_int, [_vp]),
     "d2r_softmax_fwd": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i32, _f, _vp]),
     "d2r_softmax_bwd": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i32, _f, _vp]),
     "d2r_pool_mean": (C.c_int, [Ptr8, _i32, _i32, _i64, _i64, _i64, _vp, _vp]),
@@ -152,6 +153,8 @@ def ptr(t) -> int:
 
 
 def stream() -> int:
+    """The current stream of the CURRENT device: callers run under ``torch.cuda.device(operand device)``
+    (autograd.py does this for every stack / cell call) and require_cuda() rejects operands of another device."""
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -167,6 +170,15 @@ def launch_count() -> int:
 
 
 def require_cuda(*tensors) -> None:
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("d2r_b200: tensors must live on a CUDA device (there is no CPU path)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"d2r_b200: operand on cuda:{t.device.index} but the current device is cuda:{cur}; "
+                               "wrap the call in torch.cuda.device(tensor.device) (kernels are launched on the "
+                               "current device's stream)")

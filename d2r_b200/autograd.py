@@ -10,10 +10,13 @@ given bf16 inputs, fp32 arithmetic otherwise -- the two modes the reference supp
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
+from torch.autograd.function import once_differentiable
 
+from . import kernels as K
 from . import lanes as LN
 from . import stack as S
 
@@ -90,16 +93,20 @@ class _BlocksFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, specs, out_counts, *tensors):
         dev = next(t.device for t in tensors if t is not None)
-        lanes, first = _block_lanes(dev, len(specs))
-        recs, all_outs, off = [], [], 0
-        for i, spec in enumerate(specs):
-            n = spec[0] + len(spec[1])
-            with lanes.lane(first + i):
-                outs, rec = _fwd_one(spec, tensors[off:off + n])
-            off += n
-            recs.append(rec)
-            all_outs.append(outs)
-        lanes.join()
+        _same_device(dev, tensors)
+        # every launch, stream lookup and allocation below refers to the operands' device, whatever the caller's
+        # current device is (the C ABI launches on the stream it is handed and never calls cudaSetDevice)
+        with _device_guard(dev):
+            lanes, first = _block_lanes(dev, len(specs))
+            recs, all_outs, off = [], [], 0
+            for i, spec in enumerate(specs):
+                n = spec[0] + len(spec[1])
+                with lanes.lane(first + i):
+                    outs, rec = _fwd_one(spec, tensors[off:off + n])
+                off += n
+                recs.append(rec)
+                all_outs.append(outs)
+            lanes.join()
         ctx.recs = recs
         ctx.dev = dev
         out_counts.extend(len(o) for o in all_outs)     # (caller-owned list: how to split the flat result)
@@ -109,19 +116,41 @@ class _BlocksFn(torch.autograd.Function):
         return tuple(o for outs in all_outs for o in outs)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, *grads):
         recs = ctx.recs
-        lanes, first = _block_lanes(ctx.dev, len(recs))
-        res: List[Optional[Tensor]] = [None, None]
-        off = 0
-        for i, rec in enumerate(recs):
-            n = len(rec["out_meta"])
-            with lanes.lane(first + i):
-                res += _bwd_one(rec, grads[off:off + n])
-            off += n
-        lanes.join()
+        if recs is None:
+            raise RuntimeError("d2r_b200: trying to backward through the stack a second time -- the saved "
+                               "activations are freed by the first backward (retain_graph is not supported)")
+        with _device_guard(ctx.dev):
+            # atomically-accumulated gradients (bias, router head, SAF) are carved out of per-stream zeroed arenas:
+            # start every backward -- of the whole stack or of a stand-alone cell / Block -- with fresh ones, so that
+            # a CUDA graph of the pass contains the memsets and replays do not accumulate onto stale values
+            K.zero_arena_reset()
+            lanes, first = _block_lanes(ctx.dev, len(recs))
+            res: List[Optional[Tensor]] = [None, None]
+            off = 0
+            for i, rec in enumerate(recs):
+                n = len(rec["out_meta"])
+                with lanes.lane(first + i):
+                    res += _bwd_one(rec, grads[off:off + n])
+                off += n
+            lanes.join()
         ctx.recs = None
         return tuple(res)
+
+
+def _device_guard(dev):
+    """Make the operands' device current for the duration of a pass (CPU devices only occur in the emulated
+    tests of tests/test_stack_emulated.py, where the kernels are replaced)."""
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
+def _same_device(dev, tensors) -> None:
+    for t in tensors:
+        if t is not None and t.device != dev:
+            raise RuntimeError(f"d2r_b200: inputs and parameters of one call must live on one device "
+                               f"(found {dev} and {t.device})")
 
 
 def _require_cuda(inputs) -> None:

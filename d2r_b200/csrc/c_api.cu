@@ -33,6 +33,8 @@ int num_sms() {
 }
 
 int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream);
+int gemm_tc_prof_slots();
+extern std::atomic<long long*> g_prof_buf;
 int gemm_simt(const d2r_gemm_args& a, cudaStream_t stream);
 
 }  // namespace d2r
@@ -43,6 +45,11 @@ int d2r_abi_version(void) { return D2R_B200_ABI_VERSION; }
 const char* d2r_build_arch(void) { return "sm_100a"; }
 const char* d2r_last_error(void) { return d2r::last_error_buf(); }
 int64_t d2r_launch_count(void) { return d2r::g_launches.load(); }
+
+int d2r_gemm_set_profile(int64_t* records) {
+  d2r::g_prof_buf.store(reinterpret_cast<long long*>(records));
+  return d2r::gemm_tc_prof_slots();
+}
 
 int d2r_gemm(const d2r_gemm_args* args, void* stream) {
   if (!args) return d2r::set_error(D2R_ERR_ARG, "gemm: null args");

@@ -14,12 +14,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace d2r {
+
+// debug probe (d2r_gemm_set_profile): device buffer of per-CTA stall records, nullptr = profiling off
+std::atomic<long long*> g_prof_buf{nullptr};
 
 namespace {
 
@@ -65,7 +69,30 @@ struct TcParams {
   int act, epilogue, c_dtype, r_dtype, atomic, act_cols, variant;
   int tma_store;   // 1: C (and c2) are written with TMA bulk tensor stores through a smem staging tile
   int debug;   // D2R_TC_DEBUG env (bring-up only): 1 = skip epilogue stores, 2 = skip the epilogue body, 4 = no TMA stores
+  long long* prof;   // d2r_gemm_set_profile: per-CTA stall record (kProfSlots int64 each), nullptr = off
 };
+
+// Per-CTA stall record written when p.prof is set (tools/gemm_stall.py reads it).  All values are SM clock cycles
+// of ONE elected thread per role: where the TMA producer, the MMA issuer and one epilogue warp spend their time.
+constexpr int kProfSlots = 16;
+enum ProfSlot {
+  PS_START = 0, PS_END, PS_PROD_WAIT_EMPTY, PS_PROD_KBLOCKS, PS_PROD_LOOP, PS_MMA_WAIT_FULL, PS_MMA_WAIT_TMEM,
+  PS_MMA_LOOP, PS_TILES, PS_EPI_WAIT_FULL, PS_EPI_LOOP, PS_PROLOGUE, PS_FIRST_FULL, PS_SMID, PS_EPI_STORE_WAIT
+};
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
+  if (on) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+__device__ __forceinline__ uint32_t smid() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 
 struct TileCoord {
   int m0, n0, zi, zo, z, kb0, kb1;
@@ -113,6 +140,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool prof = p.prof != nullptr;
+  long long* rec = prof ? p.prof + static_cast<long long>(blockIdx.x) * kProfSlots : nullptr;
+  const long long t_entry = prof ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -149,12 +179,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0, nkb = 0;
+      const long long t_loop = prof ? clock64() : 0;
       for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t, BN);
         const int azi = p.a_bcast_i ? 0 : tc.zi, azo = p.a_bcast_o ? 0 : tc.zo;
         const int bzi = p.b_bcast_i ? 0 : tc.zi, bzo = p.b_bcast_o ? 0 : tc.zo;
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_timed(&empty_bar[stage], phase ^ 1, prof, w_empty);
+          ++nkb;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -178,6 +211,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if (prof) {
+        rec[PS_PROD_WAIT_EMPTY] = w_empty;
+        rec[PS_PROD_KBLOCKS] = nkb;
+        rec[PS_PROD_LOOP] = clock64() - t_loop;
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -188,13 +226,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_full = 0, w_tmem = 0, ntiles = 0, first_full = -1;
+      const long long t_loop = prof ? clock64() : 0;
       for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t, BN);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_timed(&tmem_empty[acc], acc_phase ^ 1, prof, w_tmem);
+        ++ntiles;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_timed(&full_bar[stage], phase, prof, w_full);
+          if (prof && first_full < 0) first_full = clock64() - t_loop;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -220,6 +262,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           acc = 0;
           acc_phase ^= 1;
         }
+      }
+      if (prof) {
+        const long long now = clock64();
+        rec[PS_START] = t_entry;
+        rec[PS_END] = now;
+        rec[PS_MMA_WAIT_FULL] = w_full;
+        rec[PS_MMA_WAIT_TMEM] = w_tmem;
+        rec[PS_MMA_LOOP] = now - t_loop;
+        rec[PS_TILES] = ntiles;
+        rec[PS_PROLOGUE] = t_loop - t_entry;
+        rec[PS_FIRST_FULL] = first_full;
+        rec[PS_SMID] = smid();
       }
     }
     __syncwarp();
@@ -324,15 +378,25 @@ cudaError_t launch_pdl(Kern kern, dim3 grid, int smem_bytes, cudaStream_t stream
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
               const TcParams& p, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device, and safe against the forward thread and autograd's backward thread racing on the first launch
+  // (setting the attribute twice is harmless; the flag is only ever raised after a successful call)
+  static std::atomic<int> attr_set[kMaxDevices];
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev].store(1, std::memory_order_release);
   }
   long long grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   D2R_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmC2, p));
@@ -361,10 +425,13 @@ template <int PAIRS, bool A_MN, bool B_MN>
 int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                const TcParams& p, cudaStream_t stream) {
   auto kern = gemm_tc2_kernel<PAIRS, A_MN, B_MN>;
-  static long long max_units = 0;
+  static std::atomic<long long> max_units_dev[kMaxDevices];   // per device; 0 = not initialised yet (see launch_tc)
+  const int dev = current_device();
+  long long max_units = max_units_dev[dev].load(std::memory_order_acquire);
   if (!max_units) {
     D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
     max_units = PAIRS == 1 ? num_sms() / 2 : max_clusters(kern, 2 * PAIRS, Tc2Cfg::SMEM_BYTES);
+    max_units_dev[dev].store(max_units, std::memory_order_release);
   }
   const long long units = p.num_tiles < max_units ? p.num_tiles : max_units;
   D2R_CUDA_OK(launch_pdl(kern, dim3((unsigned)(2 * PAIRS * units)), Tc2Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmC2, p));
@@ -391,6 +458,8 @@ int launch_tc_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensor
 }
 
 }  // namespace
+
+int gemm_tc_prof_slots() { return kProfSlots; }
 
 int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
   D2R_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0 && a.batch > 0 && a.batch_inner > 0, "gemm: empty problem");
@@ -468,6 +537,7 @@ int gemm_tc(const d2r_gemm_args& a, cudaStream_t stream) {
     if (dbg < 0) { const char* e = getenv("D2R_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
+  p.prof = g_prof_buf.load(std::memory_order_relaxed);
   D2R_CHECK_ARG(a.act_cols % 8 == 0, "gemm: act_cols must be a multiple of 8");
   if (atomic) {
     p.variant = EV_ATOMIC;

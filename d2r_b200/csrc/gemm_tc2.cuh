@@ -56,6 +56,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const long long pair = blockIdx.x / (2 * PAIRS);  // cluster index: one BM*2*PAIRS x 256 tile at a time
   const long long npairs = gridDim.x / (2 * PAIRS);
   constexpr uint16_t kAllCtas = PAIRS == 2 ? 0xF : 0x3;
+  const bool prof = p.prof != nullptr;
+  long long* rec = prof ? p.prof + static_cast<long long>(blockIdx.x) * kProfSlots : nullptr;
+  const long long t_entry = prof ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -91,6 +94,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0, nkb = 0;
+      const long long t_loop = prof ? clock64() : 0;
       for (long long t = pair; t < p.num_tiles; t += npairs) {
         const TileCoord tc = decode_tile(p, t, BN);
         const int m0 = tc.m0 + static_cast<int>(pr) * 2 * BM + static_cast<int>(rank) * BM;
@@ -100,7 +105,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // (an explicit TMA L2 prefetch of the next tile's A rows was measured and made every shape slower:
         //  it competes with the demand loads for the same L2 request bandwidth)
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_timed(&empty_bar[stage], phase ^ 1, prof, w_empty);
+          ++nkb;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -132,6 +138,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+      if (prof) {
+        rec[PS_PROD_WAIT_EMPTY] = w_empty;
+        rec[PS_PROD_KBLOCKS] = nkb;
+        rec[PS_PROD_LOOP] = clock64() - t_loop;
+        if (rank != 0) {
+          rec[PS_START] = t_entry;
+          rec[PS_SMID] = smid();
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -143,13 +158,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_full = 0, w_tmem = 0, ntiles = 0, first_full = -1;
+      const long long t_loop = prof ? clock64() : 0;
       for (long long t = pair; t < p.num_tiles; t += npairs) {
         const TileCoord tc = decode_tile(p, t, BN);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_timed(&tmem_empty[acc], acc_phase ^ 1, prof, w_tmem);
+        ++ntiles;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_timed(&full_bar[stage], phase, prof, w_full);
+          if (prof && first_full < 0) first_full = clock64() - t_loop;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -170,6 +189,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         umma_commit_2sm(&tmem_full[acc], my_pair);      // accumulator complete -> both epilogues of this pair
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      if (prof) {
+        const long long now = clock64();
+        rec[PS_START] = t_entry;
+        rec[PS_END] = now;
+        rec[PS_MMA_WAIT_FULL] = w_full;
+        rec[PS_MMA_WAIT_TMEM] = w_tmem;
+        rec[PS_MMA_LOOP] = now - t_loop;
+        rec[PS_TILES] = ntiles;
+        rec[PS_PROLOGUE] = t_loop - t_entry;
+        rec[PS_FIRST_FULL] = first_full;
+        rec[PS_SMID] = smid();
       }
     }
     __syncwarp();

@@ -265,6 +265,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
   int acc = 0;
   uint32_t acc_phase = 0;
   const bool use_tma = p.tma_store != 0;
+  const bool prof = p.prof != nullptr && q == 0 && half == 0 && lane == 0;
+  long long w_full = 0;
+  const long long t_loop = prof ? clock64() : 0;
   for (long long t = w.first; t < p.num_tiles; t += w.step) {
     const TileCoord tc = decode_tile(p, t, BN);
     // stage this tile's bias slice in shared memory while the accumulator is still being produced
@@ -273,7 +276,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       for (int i = lane; i < BN; i += 32) sbias_warp[i] = (tc.n0 + i < p.n) ? __ldg(bias + tc.n0 + i) : 0.f;
     }
     __syncwarp();
-    mbar_wait(&tmem_full[acc], acc_phase);
+    mbar_wait_timed(&tmem_full[acc], acc_phase, prof, w_full);
     tc_fence_after();
     const int row0 = tc.m0 + w.m_off + q * 32;
     const long long row = row0 + lane;
@@ -510,6 +513,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       acc = 0;
       acc_phase ^= 1;
     }
+  }
+  if (prof) {
+    long long* rec = p.prof + static_cast<long long>(blockIdx.x) * kProfSlots;
+    rec[PS_EPI_WAIT_FULL] = w_full;
+    rec[PS_EPI_LOOP] = clock64() - t_loop;
   }
   if (lane == 0) bulk_wait_all();          // all bulk stores of this warp are complete before the CTA exits
   __syncwarp();

@@ -49,14 +49,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (kernel fails with an error) instead of hanging the GPU.  The bound is
+// generous -- 2^28 polls of a try_wait that itself suspends the thread for a while, i.e. minutes, far beyond any
+// time-slice another context can take from this one -- and -DD2R_NO_TRAP removes it altogether.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef D2R_NO_TRAP
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#else
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
+    if (++spins > (1u << 28)) {
       __trap();
     }
   }
+#endif
 }
 
 // ------------------------------------------------------------------ TMA

@@ -54,7 +54,8 @@ class GradAllReducer:
         all-reduce is launched at once (async, NCCL's stream), so it runs under the backward of the earlier
         layers and of the other stack.  ``wait()`` joins them; the pattern is capturable in a CUDA graph.
     The flat bucket is ordered by completion (module, layer in backward order), so both ways end in the same
-    state: ``p.grad`` views of one reduced buffer.
+    state: every live ``p.grad`` is a view of one reduced buffer (``finish()`` / ``wait()`` re-point them, since
+    autograd assigns the local gradients to ``p.grad`` during ``backward()``).
     """
 
     def __init__(self, modules: Iterable[torch.nn.Module], group: Optional[dist.ProcessGroup] = None):
@@ -82,6 +83,7 @@ class GradAllReducer:
         self._views: Optional[List[torch.Tensor]] = None
         self._works: list = []
         self._filled = 0
+        self._pending_div = False
         self.active = True                    # install()ed callbacks do nothing while this is False
 
     # ------------------------------------------------------------------ shared
@@ -99,8 +101,19 @@ class GradAllReducer:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _reduce(self, t: torch.Tensor, async_op: bool):
+        if not t.is_cuda:
+            self._pending_div = True          # gloo has no AVG: sum now, divide exactly once in _settle()
         return dist.all_reduce(t, op=dist.ReduceOp.AVG if t.is_cuda else dist.ReduceOp.SUM, group=self.group,
                                async_op=async_op)
+
+    def _settle(self) -> None:
+        """After the collective(s) of a step: finish the mean on gloo and make every live p.grad a view of the
+        reduced bucket (autograd has set p.grad to the local, un-reduced tensors during backward)."""
+        if self._pending_div:
+            self.flat.div_(dist.get_world_size(self.group))
+            self._pending_div = False
+        for p, v in zip(self.params, self._views):
+            p.grad = v
 
     # ------------------------------------------------------------------ one collective per step
     def pack(self) -> torch.Tensor:
@@ -119,11 +132,8 @@ class GradAllReducer:
         return self._reduce(self.flat, async_op)
 
     def finish(self) -> None:
-        """Point p.grad at the reduced bucket (gloo has no AVG: divide here)."""
-        if not self.flat.is_cuda and dist.is_initialized():
-            self.flat.div_(dist.get_world_size(self.group))
-        for p, v in zip(self.params, self._views):
-            p.grad = v
+        """Point p.grad at the reduced bucket (idempotent: the gloo division happens once per reduction)."""
+        self._settle()
 
     def step(self) -> None:
         self.pack()
@@ -166,8 +176,7 @@ class GradAllReducer:
         for w in self._works:
             w.wait()
         self._works, self._filled = [], 0
-        if not self.flat.is_cuda and self._distributed():
-            self.flat.div_(dist.get_world_size(self.group))
+        self._settle()                        # p.grad -> views of the reduced bucket, as after step()
 
 
 class InputPrefetcher:

@@ -90,6 +90,13 @@ typedef struct d2r_gemm_args {
 
 int d2r_gemm(const d2r_gemm_args* args, void* stream);
 
+/* Debug probe of the tensor-core GEMM (tools/gemm_stall.py; the one piece of process-global state besides
+ * the launch counter): while `records` is non-null every d2r_gemm(D2R_BF16) launch writes one record of
+ * `return value` int64 slots per CTA (grid <= 148 CTAs) into it -- SM-clock cycles its TMA producer spent
+ * waiting for a free shared-memory stage, its MMA issuer waiting for operands / for a free TMEM accumulator,
+ * and one epilogue warp waiting for an accumulator.  Pass NULL to switch it off (the default). */
+int d2r_gemm_set_profile(int64_t* records);
+
 /* Row softmax over the last dim, optional scale: y = softmax(scale * x).  x fp32 or bf16
  * [rows, cols] with row stride ldx; y bf16 or fp32 with row stride ldy.
  * SelfAttention.py:33-37, XModules.py:306-309, Cells.py:244-245.  */

@@ -182,8 +182,17 @@ def _dp_layerwise_worker(rank, world, port, q):
         hook = m.__dict__[LAYER_HOOK_ATTR]
         for layer in ("dynamic_itr_l2", "dynamic_itr_l1.1", "dynamic_itr_l1.0", "dynamic_itr_l0"):
             hook(layer, grads[mi])
+    # autograd leaves the LOCAL gradients in p.grad during backward; wait() must re-point them at the reduced bucket
+    for mi, m in enumerate(mods):
+        for n, p in m.named_parameters():
+            p.grad = grads[mi][n].clone()
     red.wait()
     layerwise = red.flat.clone()
+    lo, hi = red.flat.data_ptr(), red.flat.data_ptr() + red.flat.numel() * 4
+    for p, v in zip(red.params, red._views):
+        assert lo <= p.grad.data_ptr() < hi and torch.equal(p.grad, v), "p.grad is not the reduced view after wait()"
+    red.finish()                          # a stray finish() after wait() must not divide a second time
+    assert torch.equal(red.flat, layerwise)
     # reference: the one-collective path on the same per-rank gradients
     for mi, m in enumerate(mods):
         for n, p in m.named_parameters():

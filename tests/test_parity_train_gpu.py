@@ -1,0 +1,346 @@
+"""Parity of the BENCHMARKED path: bf16 backward, the config-2 shape (B=64 / 256, 128 + 50 tokens, R=3, train mode,
+both branches through run_pair under a CUDA graph) and the real 3-way argmax (stack -> CLS poolers -> Block -> fc).
+
+VERDICT r1 "Next round" item 1.  Everything goes nn.Module -> ctypes -> C ABI -> sm_100a kernels; the checker is
+the CPU oracle (oracle/d2r_oracle.py, pinned on reference-generated goldens by tests/test_oracle.py) run with torch
+autograd on the same seeded inputs and weights.
+
+Gradient metrics.  Max-norm errors of gradients are dominated by a handful of elements behind
+softmax(100 q.k / sqrt(768)), so gradients are judged by relative L2 error and cosine similarity per tensor:
+  fp32 mode   rel-L2 <= 5e-3 (measured ~1e-5 .. 1e-4), cosine >= 0.9999
+  bf16 mode   rel-L2 <= 5e-2 and cosine >= 0.995 on the small golden cases;
+              at the benchmark shape bf16 operand rounding (2^-8) moves a cross-modal logit (|100 q.k/sqrt(768)| ~ 50)
+              by ~0.2, which no bf16 implementation can avoid -- the REFERENCE's own autocast(bf16) run differs from
+              its fp32 run by the same amount -- so there the bound is max(5e-2, 2 x the error of the oracle run
+              under torch.autocast("cpu", bfloat16) against the fp32 oracle), with that yardstick computed in the
+              test and written next to the measured value in gpurun_out/parity_report.json.
+Mathematically-zero gradients (O.is_zero_grad_param) are excluded; dead parameters must have grad None."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import d2r_oracle as O
+from tests.golden.cases import CASES, PARAM_SEED_BASE, INPUT_SEED_BASE, LOSS_SEED
+from tests.test_parity_gpu import GOLD, build, make_args, relerr
+
+pytestmark = pytest.mark.gpu
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.json")
+
+
+def l2rel(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu().flatten(), torch.as_tensor(b).detach().double().cpu().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+def cosine(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu().flatten(), torch.as_tensor(b).detach().double().cpu().flatten()
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-300)).item()
+
+
+def report(key, value):
+    try:
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        data = json.load(open(REPORT)) if os.path.exists(REPORT) else {}
+        data[key] = value
+        json.dump(data, open(REPORT, "w"), indent=1, sort_keys=True)
+    except Exception:
+        pass
+
+
+def oracle_run(P, text, image, R, rev, training, w_out=None, w_sim=None, autocast=False):
+    """Oracle forward + backward -> (out, sim, probs, d_text, d_image, {param: grad}).  Fresh leaves every call."""
+    Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and not O.is_dead_param(k)
+              else v.clone()) for k, v in P.items()}
+    t, i = text.clone().requires_grad_(True), image.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+        out, sim, probs = O.stack_forward(Pl, t, i, R, 6, rev, training, {})
+    o = out[0].float()
+    loss = (o * w_out).sum() if w_out is not None else o.sum()
+    loss = loss + ((sim.float() * w_sim).sum() if w_sim is not None else sim.float().sum())
+    loss.backward()
+    grads = {k: v.grad for k, v in Pl.items() if v.requires_grad and v.grad is not None}
+    return o.detach(), sim.detach().float(), [p.detach().float() for p in probs], t.grad, i.grad, grads
+
+
+def grad_metrics(named_got, named_ref, training):
+    """Per-tensor and global (all live gradients concatenated) errors against the fp32 oracle.
+    -> ({name: (rel-L2, cosine)}, global rel-L2, global cosine); mathematically-zero gradients excluded."""
+    per, num, den, dot, ng = {}, 0.0, 0.0, 0.0, 0.0
+    for k, ref in named_ref.items():
+        if O.is_zero_grad_param(k, training) or ref.norm().item() == 0.0:
+            continue
+        got = named_got[k].detach().double().cpu().flatten()
+        r = ref.detach().double().flatten()
+        per[k] = (((got - r).norm() / r.norm()).item(), (torch.dot(got, r) / (got.norm() * r.norm() + 1e-300)).item())
+        num += float((got - r).pow(2).sum())
+        den += float(r.pow(2).sum())
+        dot += float(torch.dot(got, r))
+        ng += float(got.pow(2).sum())
+    return per, (num / den) ** 0.5, dot / ((ng * den) ** 0.5 + 1e-300)
+
+
+def check_param_grads(tag, got, ref_f32, ref_autocast, training, bf16):
+    """fp32: every tensor within 5e-3 / cosine 0.9999.  bf16: the global gradient within max(5e-2, 2 x yardstick)
+    and cosine >= 0.995 (or the yardstick's), every tensor within max(5e-2, 2 x ITS yardstick): a few tiny
+    gradients (query/key biases behind the softmax, BatchNorm(1) affine) are differences of large terms and carry
+    O(1) relative error in ANY bf16 evaluation, the reference's own autocast run included."""
+    per, gl2, gcos = grad_metrics(got, ref_f32, training)
+    worst = max(per.items(), key=lambda kv: kv[1][0])
+    rep = dict(global_l2rel=gl2, global_cos=gcos, worst=[worst[0], worst[1][0], worst[1][1]],
+               tensors=len(per), tensors_within_5e_2=sum(1 for v in per.values() if v[0] <= 5e-2))
+    if not bf16:
+        assert gl2 <= 1e-3 and gcos >= 0.99999, (tag, gl2, gcos)
+        for k, (e, c) in per.items():
+            assert e <= 5e-3 and c >= 0.9999, (tag, k, e, c)
+        return rep
+    yper, yl2, ycos = grad_metrics(ref_autocast, ref_f32, training)
+    rep.update(ref_autocast_global_l2rel=yl2, ref_autocast_global_cos=ycos,
+               ref_autocast_tensors_within_5e_2=sum(1 for v in yper.values() if v[0] <= 5e-2))
+    assert gl2 <= max(5e-2, 2 * yl2), (tag, "global gradient", gl2, yl2)
+    assert gcos >= min(0.995, 1 - 2 * (1 - ycos)), (tag, "global cosine", gcos, ycos)
+    for k, (e, c) in per.items():
+        assert e <= max(5e-2, 2 * yper[k][0]), (tag, k, e, yper[k][0])
+    return rep
+
+
+# ------------------------------------------------------------------------------ (i) bf16 backward, golden cases
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_bf16_backward_against_reference_golden_and_oracle(case):
+    """The mode bench.py times (autocast bf16): input gradients against the REFERENCE goldens, every live parameter
+    gradient against the oracle's autograd on the same inputs, and the parameter-gradient digests of the goldens."""
+    name, B, Lt, Li, R, rev, training, realistic, scale = case
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    P = O.make_params(PARAM_SEED_BASE + R, R, 6, scale)
+    m = build(R, 6, rev, P, training)
+    text, image = O.make_inputs(INPUT_SEED_BASE + B, B, Lt, Li, realistic=realistic)
+    g = torch.Generator().manual_seed(LOSS_SEED)
+    w_out = torch.randn(gold["out"].shape, generator=g)
+    w_sim = torch.randn(gold["sim"].shape, generator=g)
+    t, i = text.cuda().requires_grad_(True), image.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out, sim, probs = m(t, i, return_path_probs=True)
+    ((out[0] * w_out.cuda()).sum() + (sim * w_sim.cuda()).sum()).backward()
+    _, _, _, rt, ri, rgrads = oracle_run(P, text, image, R, rev, training, w_out, w_sim)
+    # the oracle's input gradients are the reference's (pinned): cross-check on the spot
+    assert relerr(rt, gold["d_text"]) <= 1e-4 and relerr(ri, gold["d_image"]) <= 1e-4
+    # yardstick: the reference algorithm's own bf16 (autocast) deviation from fp32 on this case
+    _, _, _, at, ai, agrads = oracle_run(P, text, image, R, rev, training, w_out, w_sim, autocast=True)
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    dead = set(gold["dead"].tolist())
+    for k, p in m.named_parameters():
+        assert (p.grad is None) == (k in dead), k
+    e_in = max(l2rel(t.grad, gold["d_text"]), l2rel(i.grad, gold["d_image"]))
+    c_in = min(cosine(t.grad, gold["d_text"]), cosine(i.grad, gold["d_image"]))
+    y_in = max(l2rel(at, rt), l2rel(ai, ri))
+    rep = dict(input_grad_l2rel=e_in, input_grad_cos=c_in, ref_autocast_input_l2rel=y_in)
+    try:
+        rep["params"] = check_param_grads(name, got, rgrads, agrads, training, True)
+    finally:
+        report(f"bf16_bwd/{name}", rep)
+    assert e_in <= max(5e-2, 2.0 * y_in), ("input gradients", e_in, y_in)
+    assert c_in >= min(0.995, 1 - 2 * (1 - min(cosine(at, rt), cosine(ai, ri)))), c_in
+    # reference digests (abs-sum of every live gradient as the unmodified reference produced them)
+    _, gl2, _ = grad_metrics(got, rgrads, training)
+    for k, gk in got.items():
+        if O.is_zero_grad_param(k, training):
+            continue
+        ref = gold["gd/" + k]
+        asum = gk.detach().double().abs().sum().item()
+        assert abs(asum - ref[1]) <= 0.5 * abs(ref[1]) + 1e-12, (k, asum, ref[1])    # gross-error guard per tensor
+
+
+# ------------------------------------------------------------------------------ (ii) config 2, train mode
+def _config2_step(mt, mi, t, i, bf16, graph):
+    from d2r_b200.interaction import run_pair
+
+    def step():
+        t.grad = None
+        i.grad = None
+        for m in (mt, mi):
+            for p in m.parameters():
+                p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            (o1, s1, p1), (o2, s2, p2) = run_pair(mt, mi, t, i, return_path_probs=True)
+        (o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()).backward()       # bench.py's loss
+        return o1[0], s1, p1, o2[0], s2, p2
+
+    if not graph:
+        return step()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = step()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    return outs
+
+
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("B", [64, 256])
+def test_config2_train_vs_oracle(B, bf16):
+    """BASELINE configs[1] as bench.py runs it: batch B per GPU, 128 text + 50 image tokens, K=6, R=3, train mode
+    (BatchNorm batch statistics), both branch stacks through run_pair, forward + backward replayed from a CUDA graph.
+    At this size the library takes the CTA-pair tcgen05 kernel (m >= 8192), split-K weight gradients, the N=4608
+    K/V fusion and the 5-lane schedule -- none of which the small golden cases reach."""
+    if B == 256 and not bf16 and os.environ.get("D2R_SKIP_SLOW"):
+        pytest.skip("slow")
+    Lt, Li, R = 128, 50, 3
+    Pt, Pi = O.make_params(2023, R, 6), O.make_params(2024, R, 6)
+    text, image = O.make_inputs(2023, B, Lt, Li)
+    mt, mi = build(R, 6, False, Pt, True), build(R, 6, True, Pi, True)
+    t, i = text.cuda().requires_grad_(True), image.cuda().requires_grad_(True)
+    o1, s1, p1, o2, s2, p2 = _config2_step(mt, mi, t, i, bf16, graph=True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    r1 = oracle_run(Pt, text, image, R, False, True)
+    r2 = oracle_run(Pi, text, image, R, True, True)
+    tol_p, tol_o = (2e-2, 5e-2) if bf16 else (2e-5, 1e-4)
+    rep = {}
+    for tag, (o, s, p), r in (("text", (o1, s1, p1), r1), ("image", (o2, s2, p2), r2)):
+        ep = max(relerr(a, b) for a, b in zip(p, r[2]))
+        rep[tag] = dict(probs=ep, sim=relerr(s, r[1]), out=relerr(o, r[0]), out_l2=l2rel(o, r[0]))
+        assert ep <= tol_p, (tag, "probs", ep)
+        assert relerr(s, r[1]) <= 2 * tol_p, (tag, "sim", relerr(s, r[1]))
+        assert relerr(o, r[0]) <= tol_o, (tag, "out", relerr(o, r[0]))
+    # gradients: d_text / d_image receive contributions from BOTH stacks
+    ref_dt, ref_di = r1[3] + r2[3], r1[4] + r2[4]
+    e_t, e_i = l2rel(t.grad, ref_dt), l2rel(i.grad, ref_di)
+    rep["input_grads"] = dict(d_text_l2rel=e_t, d_image_l2rel=e_i, cos=min(cosine(t.grad, ref_dt), cosine(i.grad, ref_di)))
+    a1 = a2 = None
+    y_in = 0.0
+    if bf16:
+        # yardstick: the reference algorithm's own bf16 mode (oracle under CPU autocast) against its fp32 run
+        a1 = oracle_run(Pt, text, image, R, False, True, autocast=True)
+        a2 = oracle_run(Pi, text, image, R, True, True, autocast=True)
+        y_in = max(l2rel(a1[3] + a2[3], ref_dt), l2rel(a1[4] + a2[4], ref_di))
+        rep["input_grads"]["ref_autocast_l2rel"] = y_in
+    try:
+        for tag, m, r, a in (("text", mt, r1, a1), ("image", mi, r2, a2)):
+            got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+            for k, p in m.named_parameters():
+                assert (p.grad is None) == O.is_dead_param(k), k
+            rep["params_" + tag] = check_param_grads(tag, got, r[5], a[5] if a is not None else None, True, bf16)
+    finally:
+        report(f"config2/B{B}/{'bf16' if bf16 else 'fp32'}", rep)
+    tol_in = max(5e-2, 2.0 * y_in) if bf16 else 5e-3
+    assert e_t <= tol_in and e_i <= tol_in, (e_t, e_i, tol_in)
+
+
+# ------------------------------------------------------------------------------ (iii) the real argmax
+def test_three_way_logits_argmax_bit_exact_fp32():
+    """'argmax predictions bit-exact on the fp32 path' on the reference's actual predictions: both stacks ->
+    text_pool / vision_pool (BertPooler on row 0, modeling_unimo.py:871-872) -> Block fusion (:884) -> fc (768 -> 3,
+    unimo_model.py:147,158) -> argmax (modules/train.py:181).  Config-1 shape (B=8, 128 + 50 tokens), eval mode."""
+    from d2r_b200.interaction.Cells import BertPooler
+    from d2r_b200.interaction.XModules import Block
+    from tests.golden.make_block_golden import BLOCK_PARAM_SEED
+    B, Lt, Li, R = 8, 128, 50, 3
+    Pt, Pi = O.make_params(11, R, 6), O.make_params(12, R, 6)
+    text, image = O.make_inputs(2023, B, Lt, Li)
+    PB = O.make_block_params(BLOCK_PARAM_SEED)
+    g = torch.Generator().manual_seed(77)
+    lin = lambda o, n: (torch.randn(o, n, generator=g) / n ** 0.5, torch.randn(o, generator=g) * 0.02)
+    (wt, bt), (wv, bv), (wf, bfc) = lin(768, 768), lin(768, 768), lin(3, 768)
+    # oracle chain
+    ro1, _, _ = O.stack_forward(Pt, text, image, R, 6, False, training=False)
+    ro2, _, _ = O.stack_forward(Pi, text, image, R, 6, True, training=False)
+    tp = O.cls_pool(ro1[0], {"p.dense.weight": wt, "p.dense.bias": bt}, "p")
+    ip = O.cls_pool(ro2[0], {"p.dense.weight": wv, "p.dense.bias": bv}, "p")
+    ref_logits = torch.nn.functional.linear(O.block_fusion(PB, tp, ip), wf, bfc)
+    # product chain
+    mt, mi = build(R, 6, False, Pt, False), build(R, 6, True, Pi, False)
+    cfg = type("Cfg", (), {"hidden_size": 768})()
+    text_pool, vision_pool = BertPooler(cfg), BertPooler(cfg)
+    text_pool.load_state_dict({"dense.weight": wt, "dense.bias": bt})
+    vision_pool.load_state_dict({"dense.weight": wv, "dense.bias": bv})
+    block = Block([768, 768], 768)
+    block.load_state_dict(PB)
+    fc = torch.nn.Linear(768, 3)
+    fc.load_state_dict({"weight": wf, "bias": bfc})
+    text_pool, vision_pool, block, fc = text_pool.cuda().eval(), vision_pool.cuda().eval(), block.cuda().eval(), fc.cuda()
+    with torch.no_grad():
+        o1, _ = mt(text.cuda(), image.cuda())
+        o2, _ = mi(text.cuda(), image.cuda())
+        logits = fc(block([text_pool(o1[0]), vision_pool(o2[0])]).float())
+    assert relerr(logits, ref_logits) <= 1e-4, relerr(logits, ref_logits)
+    margin = ref_logits.sort(-1).values
+    assert (margin[:, -1] - margin[:, -2]).min().item() > 1e-3 * ref_logits.abs().max().item()   # no near-ties
+    assert torch.equal(logits.argmax(-1).cpu(), ref_logits.argmax(-1))
+
+
+# ------------------------------------------------------------------------------ arena / graph replay
+@pytest.mark.parametrize("which", ["cell", "block"])
+def test_standalone_backward_replays_from_a_cuda_graph(which):
+    """A stand-alone cell / Block backward captured in a CUDA graph must give the eager gradients on EVERY replay
+    (the atomically-accumulated bias / router-head gradients come from zero-initialised arenas whose memset has to
+    be part of the graph)."""
+    from d2r_b200.interaction.XModules import Block
+    from tests.golden.make_block_golden import BLOCK_PARAM_SEED
+    torch.manual_seed(0)
+    if which == "cell":
+        m = build(3, 6, False, O.make_params(5, 3, 6), True).dynamic_itr_l0.cmrc
+        xs = [torch.randn(4, 16, 768, device="cuda", requires_grad=True),
+              torch.randn(4, 6, 768, device="cuda", requires_grad=True)]
+        call = lambda: m(xs[0], xs[1])
+        loss = lambda r: r[0].sum() + r[1].sum()
+    else:
+        m = Block([768, 768], 768)
+        m.load_state_dict(O.make_block_params(BLOCK_PARAM_SEED))
+        m = m.cuda()
+        xs = [torch.tanh(torch.randn(8, 768, device="cuda")).requires_grad_(True),
+              torch.tanh(torch.randn(8, 768, device="cuda")).requires_grad_(True)]
+        call = lambda: m(xs)
+        loss = lambda r: r.float().sum()
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        for x in xs:
+            x.grad = None
+        loss(call()).backward()
+
+    step()
+    torch.cuda.synchronize()
+    eager = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        scale = eager[k].abs().max().item() + 1e-12
+        assert (p.grad - eager[k]).abs().max().item() <= 1e-4 * scale, (which, k)
+
+
+def test_module_on_a_non_current_device():
+    """the module may live on cuda:1 while the current device is cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    P = O.make_params(5, 3, 6)
+    text, image = O.make_inputs(11, 2, 8, 5)
+    ref, _, _ = O.stack_forward(P, text, image, 3, 6, False, training=False)
+    from d2r_b200.interaction import InteractionModule
+    m = InteractionModule(make_args(), 3, 6, 128)
+    m.load_state_dict(P)
+    m = m.to("cuda:1").eval()
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        out, _ = m(text.to("cuda:1"), image.to("cuda:1"))
+    assert relerr(out[0], ref[0]) <= 1e-4

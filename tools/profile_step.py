@@ -22,14 +22,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--config", default="stack", choices=["stack", "deep"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_breakdown.txt"))
     a = ap.parse_args()
     dev = torch.device("cuda")
     torch.manual_seed(2023)
-    mt = InteractionModule(bench.make_args(), bench.R, bench.KC, 128).to(dev).train()
-    mi = Reversed_InteractionModule(bench.make_args(), bench.R, bench.KC, 128).to(dev).train()
-    text = torch.randn(a.batch, bench.LT, bench.D, device=dev, requires_grad=True)
-    image = torch.randn(a.batch, bench.LI, bench.D, device=dev, requires_grad=True)
+    cfg = bench.CONFIGS[a.config]
+    mt = InteractionModule(bench.make_args(), cfg["R"], bench.KC, 128).to(dev).train()
+    mi = Reversed_InteractionModule(bench.make_args(), cfg["R"], bench.KC, 128).to(dev).train()
+    text = torch.randn(a.batch, cfg["Lt"], bench.D, device=dev, requires_grad=True)
+    image = torch.randn(a.batch, cfg["Li"], bench.D, device=dev, requires_grad=True)
 
     def step():
         for m in (mt, mi):
