@@ -8,10 +8,14 @@
 //     in the same pass (forward) and its gradient consumed in the same pass (backward);
 //   * the gated skip of the final layer (:108-111) reads / writes a cell input only for samples whose
 //     gate is actually set (p_j < 1e-4/K: essentially never), see d2r_gate_skip_bwd.
-// Grid (D/128, B): a block owns 128 columns of one sample and walks all L rows (4 warps, two rows in
-// flight per warp), so the reductions over L (pooled means, broadcast-cell gradients, dP) need no
-// second pass.  The set of broadcast cells is a compile-time mask (cells 1 and 5 of emb_lst), which
-// keeps the per-thread state in registers.
+//
+// Layout (round 2): every global access is 16 bytes -- a lane owns V = 16/sizeof(T) consecutive columns (8 bf16 or
+// 4 fp32), a warp 32*V columns (512 bytes per row), a block of 4 warps owns those columns of ONE sample and walks
+// all L rows, so the reductions over L (pooled means, broadcast-cell gradients, dP) need no second pass.  Per-thread
+// state is kept small -- the pooled means are rebuilt from the column sums of the 4 full cells instead of 6
+// per-output accumulators -- so that 4 blocks are resident per SM (forward) with 8 x 16 B loads in flight per
+// thread: round 1's 8-byte / 168-register version had 24 KB in flight per SM and stopped at 0.42 of the HBM peak.
+// The set of broadcast cells is a compile-time mask (cells 1 and 5 of emb_lst).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -20,31 +24,61 @@ namespace {
 
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCols = 128;   // columns per block (lane owns 4 consecutive)
 
-__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int V = 4;
+  using Raw = float4;
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+  static __device__ __forceinline__ Raw pack(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int V = 8;
+  using Raw = uint4;
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ Raw pack(const float (&v)[8]) {
+    Raw r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return r;
+  }
+};
+template <typename T> __device__ __forceinline__ typename Vec<T>::Raw ldraw(const T* p) {
+  return *reinterpret_cast<const typename Vec<T>::Raw*>(p);
 }
-__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+// outputs are written once and next read by a GEMM of the following layer, after several hundred MB of other
+// traffic: streaming (evict-first) stores keep them from displacing the operands still being read
+template <typename T> __device__ __forceinline__ void straw(T* p, const typename Vec<T>::Raw& r) {
+  __stcs(reinterpret_cast<typename Vec<T>::Raw*>(p), r);
 }
-__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+template <int V> __device__ __forceinline__ void ldf(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int q = 0; q < V; q += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p + q);
+    v[q] = a.x; v[q + 1] = a.y; v[q + 2] = a.z; v[q + 3] = a.w;
+  }
 }
-__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
-  uint2 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-  h[0] = __floats2bfloat162_rn(v[0], v[1]);
-  h[1] = __floats2bfloat162_rn(v[2], v[3]);
-  *reinterpret_cast<uint2*>(p) = u;
+template <int V> __device__ __forceinline__ void stf(float* p, const float (&v)[V]) {
+#pragma unroll
+  for (int q = 0; q < V; q += 4) *reinterpret_cast<float4*>(p + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
 }
 
 // broadcast cells of emb_lst: GLAC (1) and, with six cells, GESC (5)
 template <int K> __host__ __device__ constexpr bool is_bcast(int j) { return j == 1 || (K == 6 && j == 5); }
+// dense index of full cell j among the full cells (K=6: cells 0,2,3,4 -> 0,1,2,3; K=4: 0,2,3 -> 0,1,2)
+template <int K> __host__ __device__ constexpr int full_idx(int j) { return j == 0 ? 0 : j - 1; }
+template <int K> constexpr int num_full() { return K == 6 ? 4 : 3; }
+// dense index of broadcast cell j among the broadcast cells (1 -> 0, 5 -> 1)
+template <int K> __host__ __device__ constexpr int bc_idx(int j) { return j == 1 ? 0 : 1; }
 
 struct AggP {
   int K, n_out;
@@ -59,88 +93,124 @@ struct AggP {
   float* dP;
 };
 
-// cross-warp sum of per-thread partials v[4] for this block's 128 columns; red: [kWarps][kCols]
-__device__ __forceinline__ void block_colsum4(float (&v)[4], float (*red)[kCols], int warp, int lane) {
+// cross-warp sum of per-thread partials v[V] for this block's columns; red: [kWarps][32*V] floats.
+// Every thread ends up with the block total of its own columns.
+template <int V>
+__device__ __forceinline__ void block_colsum(float (&v)[V], float* red, int warp, int lane) {
+  constexpr int CB = 32 * V;
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = v[q];
+  for (int q = 0; q < V; ++q) red[warp * CB + lane * V + q] = v[q];
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < V; ++q) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += red[w][lane * 4 + q];
+    for (int w = 0; w < kWarps; ++w) s += red[w * CB + lane * V + q];
     v[q] = s;
   }
 }
 
 // ------------------------------------------------------------------ forward, non-final
 template <typename T, int K>
-__global__ void __launch_bounds__(kThreads) agg_fwd_kernel(const AggP p) {
+__global__ void __launch_bounds__(kThreads, 3) agg_fwd_kernel(const AggP p) {
+  constexpr int V = Vec<T>::V, CB = 32 * V, NF = num_full<K>();
+  using Raw = typename Vec<T>::Raw;
   __shared__ float sP[K * K];
   __shared__ float sG[K];
-  __shared__ float red[kWarps][kCols];
+  __shared__ __align__(16) float sBC[K * CB];     // per output: contribution of the broadcast cells (constant over L)
+  __shared__ __align__(16) float red[kWarps * CB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.y;
-  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  const long long col = (long long)blockIdx.x * CB + lane * V;
   if (threadIdx.x < K * K) sP[threadIdx.x] = p.P[b * K * K + threadIdx.x];
   if (threadIdx.x < K) sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
   __syncthreads();
-  const bool active = col < p.D;
-  // contribution of the broadcast cells to output i is constant over the rows
-  float bc[K][4], pool[K][4];
-#pragma unroll
-  for (int i = 0; i < K; ++i)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { bc[i][q] = 0.f; pool[i][q] = 0.f; }
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      if (is_bcast<K>(j)) {
-        float v[4];
-        load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, v);
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bc[i][q] = fmaf(sP[i * K + j], v[q], bc[i][q]);
-      }
-    }
-    const long long base = b * p.L * p.D + col;
-#pragma unroll 2
-    for (long long l = warp; l < p.L; l += kWarps) {
-      const long long off = base + l * p.D;
-      float e[K][4];
+  for (int idx = threadIdx.x; idx < K * CB; idx += kThreads) {
+    const int i = idx / CB, c = idx % CB;
+    const long long gc = (long long)blockIdx.x * CB + c;
+    float a = 0.f;
+    if (gc < p.D) {
 #pragma unroll
       for (int j = 0; j < K; ++j)
-        if (!is_bcast<K>(j)) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
+        if (is_bcast<K>(j)) a = fmaf(sP[i * K + j], static_cast<const float*>(p.bvec.p[j])[b * p.D + gc], a);
+    }
+    sBC[idx] = a;
+  }
+  __syncthreads();
+  const bool active = col < p.D;
+  float cs[NF][V];                // column sums over this thread's rows of the full cells (relu applied to cell 0)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) e[0][q] = fmaxf(e[0][q], 0.f);   // RIC: relu(x)
+  for (int j = 0; j < NF; ++j)
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        float v[4];
+    for (int q = 0; q < V; ++q) cs[j][q] = 0.f;
+  if (active) {
+    const long long base = b * p.L * p.D + col;
+    // two rows per iteration: 2 * NF 16-byte loads are issued before the first is consumed
+    for (long long l = warp; l < p.L; l += 2 * kWarps) {
+      const bool two = l + kWarps < p.L;
+      Raw r[2][NF];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a = fmaf(sG[i], e[0][q], bc[i][q]);
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const long long off = base + (l + h * kWarps) * p.D;
 #pragma unroll
-          for (int j = 0; j < K; ++j)
-            if (!is_bcast<K>(j)) a = fmaf(sP[i * K + j], e[j][q], a);
-          v[q] = a;
-          pool[i][q] += a;
+        for (int j = 0; j < K; ++j)
+          if (!is_bcast<K>(j)) r[h][full_idx<K>(j)] = ldraw<T>(static_cast<const T*>(p.full.p[j]) + off);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const long long off = base + (l + h * kWarps) * p.D;
+        float e[NF][V];
+#pragma unroll
+        for (int j = 0; j < NF; ++j) Vec<T>::unpack(r[h][j], e[j]);
+#pragma unroll
+        for (int q = 0; q < V; ++q) e[0][q] = fmaxf(e[0][q], 0.f);   // RIC: relu(x)
+#pragma unroll
+        for (int j = 0; j < NF; ++j)
+#pragma unroll
+          for (int q = 0; q < V; ++q) cs[j][q] += e[j][q];
+#pragma unroll 2
+        for (int i = 0; i < K; ++i) {
+          float v[V];
+          ldf<V>(&sBC[i * CB + lane * V], v);
+          // coefficient of full cell 0 includes the gated skip (gate_i * emb_0, DynamicInteraction.py:57,66)
+          const float c0 = sP[i * K] + sG[i];
+#pragma unroll
+          for (int q = 0; q < V; ++q) v[q] = fmaf(c0, e[0][q], v[q]);
+#pragma unroll
+          for (int j = 1; j < K; ++j) {
+            if (is_bcast<K>(j)) continue;
+            const float c = sP[i * K + j];
+#pragma unroll
+            for (int q = 0; q < V; ++q) v[q] = fmaf(c, e[full_idx<K>(j)][q], v[q]);
+          }
+          straw<T>(static_cast<T*>(const_cast<void*>(p.out.p[i])) + off, Vec<T>::pack(v));
         }
-        store4(static_cast<T*>(const_cast<void*>(p.out.p[i])) + off, v);
       }
     }
   }
   if (p.pooled) {
+    // mean_L(out_i) = sum_j coef_ij * mean_L(e_j) + the broadcast cells' contribution (constant over L)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) block_colsum<V>(cs[j], red, warp, lane);
     const float invL = 1.f / (float)p.L;
+    if (active) {
+      for (int i = warp; i < K; i += kWarps) {
+        float v[V];
+        ldf<V>(&sBC[i * CB + lane * V], v);
+        const float c0 = (sP[i * K] + sG[i]) * invL;
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      block_colsum4(pool[i], red, warp, lane);
-      if (warp == 0 && active) {
-        float v[4];
+        for (int q = 0; q < V; ++q) v[q] = fmaf(c0, cs[0][q], v[q]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = pool[i][q] * invL;
-        store4(p.pooled + ((long long)i * p.B + b) * p.D + col, v);
+        for (int j = 1; j < K; ++j) {
+          if (is_bcast<K>(j)) continue;
+          const float c = sP[i * K + j] * invL;
+#pragma unroll
+          for (int q = 0; q < V; ++q) v[q] = fmaf(c, cs[full_idx<K>(j)][q], v[q]);
+        }
+        stf<V>(p.pooled + ((long long)i * p.B + b) * p.D + col, v);
       }
     }
   }
@@ -148,12 +218,14 @@ __global__ void __launch_bounds__(kThreads) agg_fwd_kernel(const AggP p) {
 
 // ------------------------------------------------------------------ forward, final layer
 template <typename T, int K>
-__global__ void __launch_bounds__(kThreads) agg_fwd_final_kernel(const AggP p) {
+__global__ void __launch_bounds__(kThreads, 4) agg_fwd_final_kernel(const AggP p) {
+  constexpr int V = Vec<T>::V, CB = 32 * V, NF = num_full<K>();
+  using Raw = typename Vec<T>::Raw;
   __shared__ float sP[K];
   __shared__ float sG[K];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.y;
-  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  const long long col = (long long)blockIdx.x * CB + lane * V;
   if (threadIdx.x < K) {
     sP[threadIdx.x] = p.P[b * K + threadIdx.x];
     sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
@@ -164,46 +236,64 @@ __global__ void __launch_bounds__(kThreads) agg_fwd_final_kernel(const AggP p) {
 #pragma unroll
   for (int j = 0; j < K; ++j) S += sP[j] + sG[j];
   const float inv = 1.f / S;
-  float bc[4] = {0.f, 0.f, 0.f, 0.f};
+  float bc[V];
+#pragma unroll
+  for (int q = 0; q < V; ++q) bc[q] = 0.f;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     if (is_bcast<K>(j)) {
-      float v[4];
-      load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, v);
+      float v[V];
+      ldf<V>(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) bc[q] = fmaf(sP[j], v[q], bc[q]);
+      for (int q = 0; q < V; ++q) bc[q] = fmaf(sP[j], v[q], bc[q]);
     }
   }
   const long long base = b * p.L * p.D + col;
-#pragma unroll 2
-  for (long long l = warp; l < p.L; l += kWarps) {
-    const long long off = base + l * p.D;
-    float e[K][4];
+  bool any_gate = false;
 #pragma unroll
-    for (int j = 0; j < K; ++j)
-      if (!is_bcast<K>(j)) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
-    float v[4];
+  for (int j = 1; j < K; ++j) any_gate = any_gate || sG[j] != 0.f;
+  for (long long l = warp; l < p.L; l += 2 * kWarps) {
+    const bool two = l + kWarps < p.L;
+    Raw r[2][NF];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      // cell 0: p_0 relu(x_0) + g_0 x_0  (full[0] is the raw layer input ref_wrd[0])
-      float a = fmaf(sP[0], fmaxf(e[0][q], 0.f), fmaf(sG[0], e[0][q], bc[q]));
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long off = base + (l + h * kWarps) * p.D;
 #pragma unroll
-      for (int j = 1; j < K; ++j)
-        if (!is_bcast<K>(j)) a = fmaf(sP[j], e[j][q], a);
-      v[q] = a;
+      for (int j = 0; j < K; ++j)
+        if (!is_bcast<K>(j)) r[h][full_idx<K>(j)] = ldraw<T>(static_cast<const T*>(p.full.p[j]) + off);
     }
 #pragma unroll
-    for (int j = 1; j < K; ++j) {
-      if (sG[j] != 0.f) {   // gated skip of cell j's input (p_j < 1e-4/K: rare)
-        float x[4];
-        load4(static_cast<const T*>(p.inputs.p[j]) + off, x);
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long off = base + (l + h * kWarps) * p.D;
+      float e[NF][V], v[V];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = fmaf(sG[j], x[q], v[q]);
+      for (int j = 0; j < NF; ++j) Vec<T>::unpack(r[h][j], e[j]);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        // cell 0: p_0 relu(x_0) + g_0 x_0  (full[0] is the raw layer input ref_wrd[0])
+        float a = fmaf(sP[0], fmaxf(e[0][q], 0.f), fmaf(sG[0], e[0][q], bc[q]));
+#pragma unroll
+        for (int j = 1; j < K; ++j)
+          if (!is_bcast<K>(j)) a = fmaf(sP[j], e[full_idx<K>(j)][q], a);
+        v[q] = a;
       }
-    }
+      if (any_gate) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] *= inv;
-    store4(static_cast<T*>(const_cast<void*>(p.out.p[0])) + off, v);
+        for (int j = 1; j < K; ++j) {
+          if (sG[j] != 0.f) {   // gated skip of cell j's input (p_j < 1e-4/K: rare)
+            float x[V];
+            Vec<T>::unpack(ldraw<T>(static_cast<const T*>(p.inputs.p[j]) + off), x);
+#pragma unroll
+            for (int q = 0; q < V; ++q) v[q] = fmaf(sG[j], x[q], v[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < V; ++q) v[q] *= inv;
+      straw<T>(static_cast<T*>(const_cast<void*>(p.out.p[0])) + off, Vec<T>::pack(v));
+    }
   }
 }
 
@@ -211,123 +301,155 @@ __global__ void __launch_bounds__(kThreads) agg_fwd_final_kernel(const AggP p) {
 // g_i = d_out_i + d_pooled_i / L.   d_e_j = sum_i P_ij g_i (+ gate_i g_i for j = 0);
 // dP_ij = sum_{l,d} g_i e_j;  d_bvec_j = sum_i P_ij sum_l g_i.
 template <typename T, int K>
-__global__ void __launch_bounds__(kThreads) agg_bwd_kernel(const AggP p) {
+__global__ void __launch_bounds__(kThreads, 3) agg_bwd_kernel(const AggP p) {
+  constexpr int V = Vec<T>::V, CB = 32 * V, NF = num_full<K>();
+  using Raw = typename Vec<T>::Raw;
   __shared__ float sP[K * K];
   __shared__ float sG[K];
-  __shared__ float sDpl[K][kCols];
-  __shared__ float red[kWarps][kCols];
+  __shared__ __align__(16) float sDpl[K * CB];
+  // sum over this thread's rows of g_i, private slot per thread: [i][q / 4][thread] float4 (conflict-free).
+  // It feeds both the broadcast cells' gradient and their dP entries; in registers it would cost K * V of them.
+  __shared__ __align__(16) float4 sGs[K * (V / 4) * kThreads];
   __shared__ float sdP[kWarps][K * K];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.y;
-  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  const long long col = (long long)blockIdx.x * CB + lane * V;
   const bool active = col < p.D;
   if (threadIdx.x < K * K) sP[threadIdx.x] = p.P[b * K * K + threadIdx.x];
   if (threadIdx.x < K) sG[threadIdx.x] = p.gate[b * K + threadIdx.x];
   const float invL = 1.f / (float)p.L;
-  for (int idx = threadIdx.x; idx < K * kCols; idx += kThreads) {
-    const int i = idx / kCols, c = idx % kCols;
-    const long long gc = (long long)blockIdx.x * kCols + c;
-    sDpl[i][c] = (p.d_pooled && gc < p.D) ? p.d_pooled[((long long)i * p.B + b) * p.D + gc] * invL : 0.f;
+  for (int idx = threadIdx.x; idx < K * CB; idx += kThreads) {
+    const int i = idx / CB, c = idx % CB;
+    const long long gc = (long long)blockIdx.x * CB + c;
+    sDpl[idx] = (p.d_pooled && gc < p.D) ? p.d_pooled[((long long)i * p.B + b) * p.D + gc] * invL : 0.f;
   }
+#pragma unroll
+  for (int s = 0; s < K * (V / 4); ++s) sGs[s * kThreads + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  float eb[K][4];      // broadcast cells' values (constant over the rows)
-  float gsum[K][4];    // sum over rows of g_i
-  float dP[K][K];
+  float dP[K][NF];     // dot products with the full cells
 #pragma unroll
-  for (int j = 0; j < K; ++j) {
+  for (int i = 0; i < K; ++i)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { eb[j][q] = 0.f; gsum[j][q] = 0.f; }
-#pragma unroll
-    for (int i = 0; i < K; ++i) dP[i][j] = 0.f;
-    if (active && is_bcast<K>(j)) load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, eb[j]);
-  }
+    for (int j = 0; j < NF; ++j) dP[i][j] = 0.f;
   if (active) {
     const long long base = b * p.L * p.D + col;
     for (long long l = warp; l < p.L; l += kWarps) {
       const long long off = base + l * p.D;
-      float e[K][4], de[K][4];
+      Raw re[NF], rg[K];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        if (!is_bcast<K>(j)) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
+      for (int j = 0; j < K; ++j)
+        if (!is_bcast<K>(j)) re[full_idx<K>(j)] = ldraw<T>(static_cast<const T*>(p.full.p[j]) + off);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) de[j][q] = 0.f;
+      for (int i = 0; i < K; ++i) rg[i] = ldraw<T>(static_cast<const T*>(p.d_out.p[i]) + off);
+      float e[NF][V], de[NF][V];
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        Vec<T>::unpack(re[j], e[j]);
+#pragma unroll
+        for (int q = 0; q < V; ++q) de[j][q] = 0.f;
       }
-      float x0pos[4];
+      float x0pos[V];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < V; ++q) {
         x0pos[q] = e[0][q] > 0.f ? 1.f : 0.f;
         e[0][q] = fmaxf(e[0][q], 0.f);
       }
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        float g[4];
-        load4(static_cast<const T*>(p.d_out.p[i]) + off, g);
+        float g[V];
+        Vec<T>::unpack(rg[i], g);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) g[q] += sDpl[i][lane * 4 + q];
+        for (int q4 = 0; q4 < V / 4; ++q4) {
+          const float4 d = *reinterpret_cast<const float4*>(&sDpl[i * CB + lane * V + q4 * 4]);
+          g[q4 * 4] += d.x; g[q4 * 4 + 1] += d.y; g[q4 * 4 + 2] += d.z; g[q4 * 4 + 3] += d.w;
+          float4 a = sGs[(i * (V / 4) + q4) * kThreads + threadIdx.x];
+          a.x += g[q4 * 4]; a.y += g[q4 * 4 + 1]; a.z += g[q4 * 4 + 2]; a.w += g[q4 * 4 + 3];
+          sGs[(i * (V / 4) + q4) * kThreads + threadIdx.x] = a;
+        }
 #pragma unroll
         for (int j = 0; j < K; ++j) {
+          if (is_bcast<K>(j)) continue;
+          const float w = sP[i * K + j] + (j == 0 ? sG[i] : 0.f);
           float dot = 0.f;
-          if (is_bcast<K>(j)) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dot = fmaf(g[q], eb[j][q], dot);
-          } else {
-            const float w = sP[i * K + j] + (j == 0 ? sG[i] : 0.f);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              de[j][q] = fmaf(w, g[q], de[j][q]);
-              dot = fmaf(g[q], e[j][q], dot);
-            }
+          for (int q = 0; q < V; ++q) {
+            de[full_idx<K>(j)][q] = fmaf(w, g[q], de[full_idx<K>(j)][q]);
+            dot = fmaf(g[q], e[full_idx<K>(j)][q], dot);
           }
-          dP[i][j] += dot;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) gsum[i][q] += g[q];
-      }
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        if (!is_bcast<K>(j)) {
-          if (j == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) de[0][q] *= x0pos[q];
-          }
-          store4(static_cast<T*>(const_cast<void*>(p.d_full.p[j])) + off, de[j]);
+          dP[i][full_idx<K>(j)] += dot;
         }
       }
+#pragma unroll
+      for (int q = 0; q < V; ++q) de[0][q] *= x0pos[q];
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (!is_bcast<K>(j))
+          straw<T>(static_cast<T*>(const_cast<void*>(p.d_full.p[j])) + off, Vec<T>::pack(de[full_idx<K>(j)]));
     }
   }
-  // broadcast-cell gradients: d_bvec_j[b,col] = sum_i P_ij * sum_l g_i
-#pragma unroll
-  for (int i = 0; i < K; ++i) block_colsum4(gsum[i], red, warp, lane);
-  if (warp == 0 && active) {
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      if (is_bcast<K>(j)) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a = 0.f;
-#pragma unroll
-          for (int i = 0; i < K; ++i) a = fmaf(sP[i * K + j], gsum[i][q], a);
-          v[q] = a;
-        }
-        store4(static_cast<float*>(const_cast<void*>(p.d_bvec.p[j])) + b * p.D + col, v);
-      }
-    }
-  }
-  // dP: warp reduce, then cross-warp via smem, one atomic per (i,j) per block
+  __syncthreads();
+  // broadcast cells: d_bvec_j[b,col] = sum_i P_ij * sum_l g_i;  dP_ij = sum_col bvec_j[col] * sum_l g_i[col].
+  // Warp 0 sums the four warps' private slots of its lane's columns.
+  float dPb[K][K - NF];
 #pragma unroll
   for (int i = 0; i < K; ++i)
 #pragma unroll
+    for (int j = 0; j < K - NF; ++j) dPb[i][j] = 0.f;
+  if (warp == 0 && active) {
+    float eb[K - NF][V], db[K - NF][V];
+#pragma unroll
     for (int j = 0; j < K; ++j) {
-      const float s = warp_sum(dP[i][j]);
-      if (lane == 0) sdP[warp][i * K + j] = s;
+      if (!is_bcast<K>(j)) continue;
+      ldf<V>(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, eb[bc_idx<K>(j)]);
+#pragma unroll
+      for (int q = 0; q < V; ++q) db[bc_idx<K>(j)][q] = 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      float gs[V];
+#pragma unroll
+      for (int q4 = 0; q4 < V / 4; ++q4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const float4 t = sGs[(i * (V / 4) + q4) * kThreads + w * 32 + lane];
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        gs[q4 * 4] = a.x; gs[q4 * 4 + 1] = a.y; gs[q4 * 4 + 2] = a.z; gs[q4 * 4 + 3] = a.w;
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (!is_bcast<K>(j)) continue;
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          db[bc_idx<K>(j)][q] = fmaf(sP[i * K + j], gs[q], db[bc_idx<K>(j)][q]);
+          dot = fmaf(eb[bc_idx<K>(j)][q], gs[q], dot);
+        }
+        dPb[i][bc_idx<K>(j)] = dot;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (is_bcast<K>(j))
+        stf<V>(static_cast<float*>(const_cast<void*>(p.d_bvec.p[j])) + b * p.D + col, db[bc_idx<K>(j)]);
+  }
+  // dP: warp reduce, then cross-warp via smem, one atomic per (i,j) per block
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float t = is_bcast<K>(j) ? dPb[i][bc_idx<K>(j)] : dP[i][full_idx<K>(j)];
+      const float sm = warp_sum(t);
+      if (lane == 0) sdP[warp][i * K + j] = sm;
+    }
+  }
   __syncthreads();
   if (threadIdx.x < K * K) {
-    float s = 0.f;
+    float sm = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += sdP[w][threadIdx.x];
-    atomicAdd(p.dP + b * K * K + threadIdx.x, s);
+    for (int w = 0; w < kWarps; ++w) sm += sdP[w][threadIdx.x];
+    atomicAdd(p.dP + b * K * K + threadIdx.x, sm);
   }
 }
 
@@ -336,14 +458,16 @@ __global__ void __launch_bounds__(kThreads) agg_bwd_kernel(const AggP p) {
 // dN = d_out / S;  d_e_j = p_j dN;  dp_j = sum dN.e_j - sum dN.out.  The gated-skip gradient
 // d_x_j = g_j dN (j >= 1) is produced by d2r_gate_skip_bwd only for samples whose gate is set.
 template <typename T, int K>
-__global__ void __launch_bounds__(kThreads) agg_bwd_final_kernel(const AggP p) {
+__global__ void __launch_bounds__(kThreads, 3) agg_bwd_final_kernel(const AggP p) {
+  constexpr int V = Vec<T>::V, CB = 32 * V, NF = num_full<K>();
+  using Raw = typename Vec<T>::Raw;
   __shared__ float sP[K];
   __shared__ float sG[K];
-  __shared__ float red[kWarps][kCols];
+  __shared__ __align__(16) float red[kWarps * CB];
   __shared__ float sdP[kWarps][K + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.y;
-  const long long col = (long long)blockIdx.x * kCols + lane * 4;
+  const long long col = (long long)blockIdx.x * CB + lane * V;
   const bool active = col < p.D;
   if (threadIdx.x < K) {
     sP[threadIdx.x] = p.P[b * K + threadIdx.x];
@@ -354,108 +478,125 @@ __global__ void __launch_bounds__(kThreads) agg_bwd_final_kernel(const AggP p) {
 #pragma unroll
   for (int j = 0; j < K; ++j) S += sP[j] + sG[j];
   const float inv = 1.f / S;
-  float eb[K][4], dp[K + 1], dnsum[4], bcN[4];
+  float eb[K - NF][V], dp[K + 1], dnsum[V], bcN[V];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { dnsum[q] = 0.f; bcN[q] = 0.f; }
+  for (int q = 0; q < V; ++q) { dnsum[q] = 0.f; bcN[q] = 0.f; }
+#pragma unroll
+  for (int j = 0; j <= K; ++j) dp[j] = 0.f;   // dp[K] = sum dN . out
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    dp[j] = 0.f;
+    if (!is_bcast<K>(j)) continue;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) eb[j][q] = 0.f;
-    if (active && is_bcast<K>(j)) {
-      load4(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, eb[j]);
+    for (int q = 0; q < V; ++q) eb[bc_idx<K>(j)][q] = 0.f;
+    if (active) {
+      ldf<V>(static_cast<const float*>(p.bvec.p[j]) + b * p.D + col, eb[bc_idx<K>(j)]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) bcN[q] = fmaf(sP[j], eb[j][q], bcN[q]);
+      for (int q = 0; q < V; ++q) bcN[q] = fmaf(sP[j], eb[bc_idx<K>(j)][q], bcN[q]);
     }
   }
-  dp[K] = 0.f;   // sum dN . out
+  bool any_gate = false;
+#pragma unroll
+  for (int j = 1; j < K; ++j) any_gate = any_gate || sG[j] != 0.f;
   if (active) {
     const long long base = b * p.L * p.D + col;
-#pragma unroll 2
-    for (long long l = warp; l < p.L; l += kWarps) {
-      const long long off = base + l * p.D;
-      float e[K][4];
+    for (long long l = warp; l < p.L; l += 2 * kWarps) {
+      const bool two = l + kWarps < p.L;
+      Raw r[2][NF + 1];
 #pragma unroll
-      for (int j = 0; j < K; ++j)
-        if (!is_bcast<K>(j)) load4(static_cast<const T*>(p.full.p[j]) + off, e[j]);
-      float dN[4], N[4], x0[4];
-      load4(static_cast<const T*>(p.d_out.p[0]) + off, dN);
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const long long off = base + (l + h * kWarps) * p.D;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dN[q] *= inv;
-        dnsum[q] += dN[q];
-        x0[q] = e[0][q];
-        e[0][q] = fmaxf(x0[q], 0.f);
-        N[q] = fmaf(sG[0], x0[q], bcN[q]);
+        for (int j = 0; j < K; ++j)
+          if (!is_bcast<K>(j)) r[h][full_idx<K>(j)] = ldraw<T>(static_cast<const T*>(p.full.p[j]) + off);
+        r[h][NF] = ldraw<T>(static_cast<const T*>(p.d_out.p[0]) + off);
       }
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        float dot = 0.f;
-        if (is_bcast<K>(j)) {
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const long long off = base + (l + h * kWarps) * p.D;
+        float e[NF][V], dN[V], N[V], x0[V];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dot = fmaf(dN[q], eb[j][q], dot);
-        } else {
+        for (int j = 0; j < NF; ++j) Vec<T>::unpack(r[h][j], e[j]);
+        Vec<T>::unpack(r[h][NF], dN);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            N[q] = fmaf(sP[j], e[j][q], N[q]);
-            dot = fmaf(dN[q], e[j][q], dot);
+        for (int q = 0; q < V; ++q) {
+          dN[q] *= inv;
+          dnsum[q] += dN[q];
+          x0[q] = e[0][q];
+          e[0][q] = fmaxf(x0[q], 0.f);
+          N[q] = fmaf(sG[0], x0[q], bcN[q]);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          float dot = 0.f;
+          if (is_bcast<K>(j)) {
+#pragma unroll
+            for (int q = 0; q < V; ++q) dot = fmaf(dN[q], eb[bc_idx<K>(j)][q], dot);
+          } else {
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+              N[q] = fmaf(sP[j], e[full_idx<K>(j)][q], N[q]);
+              dot = fmaf(dN[q], e[full_idx<K>(j)][q], dot);
+            }
+          }
+          dp[j] += dot;
+        }
+        if (any_gate) {
+#pragma unroll
+          for (int j = 1; j < K; ++j) {
+            if (sG[j] != 0.f) {
+              float x[V];
+              Vec<T>::unpack(ldraw<T>(static_cast<const T*>(p.inputs.p[j]) + off), x);
+#pragma unroll
+              for (int q = 0; q < V; ++q) N[q] = fmaf(sG[j], x[q], N[q]);
+            }
           }
         }
-        dp[j] += dot;
-      }
+        {
+          float dot = 0.f;
 #pragma unroll
-      for (int j = 1; j < K; ++j) {
-        if (sG[j] != 0.f) {
-          float x[4];
-          load4(static_cast<const T*>(p.inputs.p[j]) + off, x);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) N[q] = fmaf(sG[j], x[q], N[q]);
+          for (int q = 0; q < V; ++q) dot = fmaf(dN[q], N[q] * inv, dot);
+          dp[K] += dot;
         }
-      }
-      {
-        float dot = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dot = fmaf(dN[q], N[q] * inv, dot);
-        dp[K] += dot;
-      }
+        for (int j = 0; j < K; ++j) {
+          if (is_bcast<K>(j)) continue;
+          float v[V];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        if (!is_bcast<K>(j)) {
-          float v[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < V; ++q)
             v[q] = j == 0 ? dN[q] * (sP[0] * (x0[q] > 0.f ? 1.f : 0.f) + sG[0]) : sP[j] * dN[q];
-          store4(static_cast<T*>(const_cast<void*>(p.d_full.p[j])) + off, v);
+          straw<T>(static_cast<T*>(const_cast<void*>(p.d_full.p[j])) + off, Vec<T>::pack(v));
         }
       }
     }
   }
-  block_colsum4(dnsum, red, warp, lane);
+  block_colsum<V>(dnsum, red, warp, lane);
   if (warp == 0 && active) {
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       if (is_bcast<K>(j)) {
-        float v[4];
+        float v[V];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = sP[j] * dnsum[q];
-        store4(static_cast<float*>(const_cast<void*>(p.d_bvec.p[j])) + b * p.D + col, v);
+        for (int q = 0; q < V; ++q) v[q] = sP[j] * dnsum[q];
+        stf<V>(static_cast<float*>(const_cast<void*>(p.d_bvec.p[j])) + b * p.D + col, v);
       }
     }
   }
 #pragma unroll
   for (int j = 0; j <= K; ++j) {
-    const float s = warp_sum(dp[j]);
-    if (lane == 0) sdP[warp][j] = s;
+    const float sm = warp_sum(dp[j]);
+    if (lane == 0) sdP[warp][j] = sm;
   }
   __syncthreads();
   if (threadIdx.x < K) {
-    float s = 0.f, t = 0.f;
+    float sm = 0.f, t = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-      s += sdP[w][threadIdx.x];
+      sm += sdP[w][threadIdx.x];
       t += sdP[w][K];
     }
-    atomicAdd(p.dP + b * K + threadIdx.x, s - t);
+    atomicAdd(p.dP + b * K + threadIdx.x, sm - t);
   }
 }
 
@@ -494,7 +635,8 @@ __global__ void __launch_bounds__(256) gate_skip_bwd_kernel(const T* __restrict_
 int fill_common(AggP& q, const d2r_agg_args& a) {
   D2R_CHECK_ARG(a.K == 4 || a.K == 6, "aggregate: K must be 4 or 6 (got %d)", a.K);
   D2R_CHECK_ARG(a.final_layer ? a.n_out == 1 : a.n_out == a.K, "aggregate: n_out must be K (or 1 in the final layer)");
-  D2R_CHECK_ARG(a.B > 0 && a.L > 0 && a.D > 0 && a.D % 4 == 0 && a.B <= 65535, "aggregate: bad shape");
+  D2R_CHECK_ARG(a.B > 0 && a.L > 0 && a.D > 0 && a.B <= 65535, "aggregate: bad shape");
+  D2R_CHECK_ARG(a.D % (a.dtype == D2R_BF16 ? 8 : 4) == 0, "aggregate: D must be a multiple of 8 (bf16) / 4 (fp32): 16-byte accesses");
   for (int j = 0; j < a.K; ++j) {
     const bool bc = a.K == 6 ? is_bcast<6>(j) : is_bcast<4>(j);
     D2R_CHECK_ARG(bc ? (a.bvec.p[j] != nullptr && a.full.p[j] == nullptr)
@@ -518,7 +660,8 @@ int d2r_aggregate_fwd(const d2r_agg_args* a, void* stream) {
   D2R_CHECK_ARG(a != nullptr, "aggregate: null args");
   AggP q{};
   if (int rc = fill_common(q, *a)) return rc;
-  dim3 grid((unsigned)((a->D + kCols - 1) / kCols), (unsigned)a->B);
+  const int cb = a->dtype == D2R_BF16 ? 256 : 128;     // columns per block: 32 lanes x 16 bytes
+  dim3 grid((unsigned)((a->D + cb - 1) / cb), (unsigned)a->B);
 #define D2R_AGG_LAUNCH(KERN)                                                         \
   do {                                                                               \
     if (a->K == 6) { D2R_DISPATCH_DTYPE(a->dtype, T, KERN<T, 6><<<grid, kThreads, 0, st>>>(q)); } \
@@ -543,7 +686,8 @@ int d2r_aggregate_bwd(const d2r_agg_bwd_args* a, void* stream) {
     D2R_CHECK_ARG(bc ? a->d_bvec.p[j] != nullptr : a->d_full.p[j] != nullptr, "aggregate_bwd: missing gradient buffer %d", j);
   }
   D2R_CUDA_OK(cudaMemsetAsync(a->dP, 0, sizeof(float) * (size_t)f->B * f->n_out * f->K, st));
-  dim3 grid((unsigned)((f->D + kCols - 1) / kCols), (unsigned)f->B);
+  const int cb = f->dtype == D2R_BF16 ? 256 : 128;
+  dim3 grid((unsigned)((f->D + cb - 1) / cb), (unsigned)f->B);
 #define D2R_AGGB_LAUNCH(KERN)                                                         \
   do {                                                                                \
     if (f->K == 6) { D2R_DISPATCH_DTYPE(f->dtype, T, KERN<T, 6><<<grid, kThreads, 0, st>>>(q)); } \
