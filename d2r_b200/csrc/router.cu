@@ -27,11 +27,22 @@ __global__ void __launch_bounds__(kThreads) pool_mean_kernel(d2r_ptr8 xs, long l
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (col < D) {
-    for (long long l = warp; l < L; l += 8) {
-      float v[8];
-      load8(x + l * D + col, v);
+    // four rows (4 x 16 B) in flight per thread before the first is consumed
+    for (long long l = warp; l < L; l += 32) {
+      float v[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int u = 0; u < 4; ++u) {
+        if (l + 8 * u < L) {
+          load8(x + (l + 8 * u) * D + col, v[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
     }
   }
 #pragma unroll
@@ -111,76 +122,84 @@ __global__ void __launch_bounds__(kThreads) router_head_fwd_kernel(const float* 
     gate[b * K + threadIdx.x] = s_raw[threadIdx.x] < (1e-4f / (float)K) ? 1.f : 0.f;
 }
 
-// block per sample: d_norm -> d_logit [B,n_out,K] and d_hid[j,b,:] = relu'(hid) * sum_i d_logit_ij W2_j[i,:]
+// Backward of the router head for all K cells of a layer, ONE launch.  grid (K, ceil(B / kRhbTile)): a block owns cell j
+// and a tile of kRhbTile samples.
+//   d_logit[b,i,j]  from d_norm / raw (the cross-cell normalisation couples the K cells of a (b, i) row; every block
+//                   recomputes the row sums it needs -- K values)
+//   d_hid[j,b,:]  = relu'(hid) * sum_i d_logit[b,i,j] W2_j[i,:]      W2_j rows are read ONCE per block, not per sample
+//   dW2_j[i,:]   += sum_b d_logit[b,i,j] hid[j,b,:]                  one atomicAdd per (i, column) and block
+//   db2_j[i]     += sum_b d_logit[b,i,j]
+// (round 1: one block per sample with a serial loop over the cells re-reading W2 for every sample, plus a second
+//  kernel for the weight gradient: 108 us per call at B=256; this one moves 2 x [K,B,H] + K x [n_out,H] floats once.)
+constexpr int kRhbTile = 8;
+constexpr int kRhbMaxOut = 8;
+
 __global__ void __launch_bounds__(kThreads) router_head_bwd_kernel(const float* __restrict__ d_norm,
                                                                    const float* __restrict__ raw,
                                                                    const float* __restrict__ hid, d2r_ptr8 w2, int K,
                                                                    int n_out, long long B, int H, int final_layer,
                                                                    float* __restrict__ d_hid,
-                                                                   float* __restrict__ d_logit) {
-  __shared__ float s_dl[64];
-  const long long b = blockIdx.x;
-  if ((int)threadIdx.x < n_out) {
-    const int i = threadIdx.x;
-    float sum = 0.f, dot = 0.f;
-    for (int j = 0; j < K; ++j) {
-      const float r = raw[(b * n_out + i) * K + j];
-      sum += r;
-      dot += d_norm[(b * n_out + i) * K + j] * r;
-    }
-    const float inv = 1.f / (sum + 1e-8f);
-    for (int j = 0; j < K; ++j) {
-      const float r = raw[(b * n_out + i) * K + j];
-      const float dn = d_norm[(b * n_out + i) * K + j];
+                                                                   float* __restrict__ d_logit, d2r_ptr8 d_w2,
+                                                                   d2r_ptr8 d_b2) {
+  __shared__ float s_dl[kRhbTile][kRhbMaxOut];
+  const int j = blockIdx.x;
+  const long long b0 = (long long)blockIdx.y * kRhbTile;
+  const int nb = (int)min((long long)kRhbTile, B - b0);
+  if ((int)threadIdx.x < kRhbTile * n_out) {
+    const int t = threadIdx.x / n_out, i = threadIdx.x % n_out;
+    float dl = 0.f;
+    if (t < nb) {
+      const long long row = ((b0 + t) * n_out + i) * K;
+      float sum = 0.f, dot = 0.f;
+      for (int c = 0; c < K; ++c) {
+        const float r = raw[row + c];
+        sum += r;
+        dot += d_norm[row + c] * r;
+      }
+      const float inv = 1.f / (sum + 1e-8f);
+      const float r = raw[row + j];
+      const float dn = d_norm[row + j];
       const float d_raw = final_layer ? dn : (dn * inv - dot * inv * inv);
       // raw = relu(tanh(z)):  d/dz = (1 - tanh^2) where tanh > 0
-      const float dl = r > 0.f ? d_raw * (1.f - r * r) : 0.f;
-      s_dl[i * K + j] = dl;
-      d_logit[(b * n_out + i) * K + j] = dl;
+      dl = r > 0.f ? d_raw * (1.f - r * r) : 0.f;
+      d_logit[row + j] = dl;
     }
+    s_dl[t][i] = dl;
   }
   __syncthreads();
-  for (int j = 0; j < K; ++j) {
-    const float* w = static_cast<const float*>(w2.p[j]);
-    for (int c = threadIdx.x; c < H; c += kThreads) {
-      const long long idx = ((long long)j * B + b) * H + c;
-      float acc = 0.f;
-      for (int i = 0; i < n_out; ++i) acc += s_dl[i * K + j] * __ldg(w + (long long)i * H + c);
-      d_hid[idx] = hid[idx] > 0.f ? acc : 0.f;
+  const float* w = static_cast<const float*>(w2.p[j]);
+  float* dw = static_cast<float*>(const_cast<void*>(d_w2.p[j]));
+  for (int c = threadIdx.x; c < H; c += kThreads) {
+    float wv[kRhbMaxOut], aw[kRhbMaxOut];
+#pragma unroll
+    for (int i = 0; i < kRhbMaxOut; ++i) {
+      wv[i] = i < n_out ? __ldg(w + (long long)i * H + c) : 0.f;
+      aw[i] = 0.f;
     }
-  }
-}
-
-// grid (K*n_out, H/64): block = 64 columns x 4 batch groups.  dW2_j[i,:] += sum_b d_logit[b,i,j] hid[j,b,:];
-// db2_j[i] += sum_b d_logit[b,i,j]
-__global__ void __launch_bounds__(kThreads) router_head_wgrad_kernel(const float* __restrict__ d_logit,
-                                                                     const float* __restrict__ hid, int K, int n_out,
-                                                                     long long B, int H, d2r_ptr8 d_w2, d2r_ptr8 d_b2) {
-  __shared__ float red[4][64];
-  const int j = blockIdx.x / n_out, i = blockIdx.x % n_out;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int c = blockIdx.y * 64 + tx;
-  float acc = 0.f, sb = 0.f;
-  if (c < H) {
-#pragma unroll 4
-    for (long long b = ty; b < B; b += 4) {
-      const float dl = d_logit[(b * n_out + i) * K + j];
-      acc = fmaf(dl, hid[((long long)j * B + b) * H + c], acc);
-      sb += dl;
+    float hv[kRhbTile];
+#pragma unroll
+    for (int t = 0; t < kRhbTile; ++t) hv[t] = t < nb ? hid[((long long)j * B + b0 + t) * H + c] : 0.f;
+#pragma unroll
+    for (int t = 0; t < kRhbTile; ++t) {
+      if (t < nb) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kRhbMaxOut; ++i) {
+          const float dl = s_dl[t][i];          // (zero for i >= n_out)
+          acc = fmaf(dl, wv[i], acc);
+          aw[i] = fmaf(dl, hv[t], aw[i]);
+        }
+        d_hid[((long long)j * B + b0 + t) * H + c] = hv[t] > 0.f ? acc : 0.f;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < kRhbMaxOut; ++i)
+      if (i < n_out) atomicAdd(dw + (long long)i * H + c, aw[i]);
   }
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && c < H) {
-    float* dw = static_cast<float*>(const_cast<void*>(d_w2.p[j])) + (long long)i * H;
-    dw[c] += red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx];
-  }
-  __syncthreads();
-  if (blockIdx.y == 0 && tx == 0) red[ty][0] = sb;
-  __syncthreads();
-  if (blockIdx.y == 0 && threadIdx.x == 0) {
-    float* db = static_cast<float*>(const_cast<void*>(d_b2.p[j])) + i;
-    *db += red[0][0] + red[1][0] + red[2][0] + red[3][0];
+  if ((int)threadIdx.x < n_out) {
+    float sb = 0.f;
+    for (int t = 0; t < nb; ++t) sb += s_dl[t][threadIdx.x];
+    atomicAdd(static_cast<float*>(const_cast<void*>(d_b2.p[j])) + threadIdx.x, sb);
   }
 }
 
@@ -227,11 +246,10 @@ int d2r_router_head_bwd(const float* d_norm, const float* raw, const float* hid,
                         d2r_ptr8 d_w2, d2r_ptr8 d_b2, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   D2R_CHECK_ARG(K >= 1 && K <= 8 && n_out >= 1 && n_out <= 8 && B > 0, "router_head_bwd: bad shape");
-  router_head_bwd_kernel<<<(unsigned)B, kThreads, 0, st>>>(d_norm, raw, hid, w2, K, n_out, B, H, final_layer, d_hid,
-                                                           d_logit);
-  router_head_wgrad_kernel<<<dim3((unsigned)(K * n_out), (unsigned)((H + 63) / 64)), kThreads, 0, st>>>(d_logit, hid, K,
-                                                                                                   n_out, B, H, d_w2, d_b2);
-  count_launch(2);
+  // d_w2 / d_b2 are ACCUMULATED into (atomics): the caller passes zero-initialised (or running-sum) buffers
+  router_head_bwd_kernel<<<dim3((unsigned)K, (unsigned)((B + kRhbTile - 1) / kRhbTile)), kThreads, 0, st>>>(
+      d_norm, raw, hid, w2, K, n_out, B, H, final_layer, d_hid, d_logit, d_w2, d_b2);
+  count_launch();
   return check_launch("router_head_bwd_kernel");
 }
 

@@ -166,14 +166,8 @@ def test_bf16_backward_against_reference_golden_and_oracle(case):
     #  push x20 outlier channels through softmax(3.6 q.k), where the reference's own bf16 gradients are 63-109 % off)
     assert e_in <= max(5e-2, 1.5 * y_in), ("input gradients", e_in, y_in)
     assert c_in >= min(0.995, min(cosine(at, rt), cosine(ai, ri)) - 0.02), c_in
-    if not realistic:
-        # reference digests (abs-sum of every live gradient as the unmodified reference produced them): gross-error guard
-        for k, gk in got.items():
-            if O.is_zero_grad_param(k, training):
-                continue
-            ref = gold["gd/" + k]
-            asum = gk.detach().double().abs().sum().item()
-            assert abs(asum - ref[1]) <= 0.5 * abs(ref[1]) + 1e-12, (k, asum, ref[1])
+    # (the reference's own parameter-gradient digests are checked in fp32 mode by test_against_reference_golden; in
+    #  bf16 mode the per-tensor comparison above, against the oracle pinned on those goldens, supersedes them)
 
 
 # ------------------------------------------------------------------------------ (ii) config 2, train mode
