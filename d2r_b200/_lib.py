@@ -38,6 +38,18 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("heads", C.c_int32), ("Lq", C.c_int32), ("Lc", C.c_int32), ("hd", C.c_int32),
+        ("mode", C.c_int32), ("alpha", C.c_float), ("reserved0", C.c_int32),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("q_ld", C.c_int64), ("k_ld", C.c_int64), ("v_ld", C.c_int64),
+        ("p", C.c_void_p), ("p_ld", C.c_int64),
+        ("out", C.c_void_p), ("out2", C.c_void_p), ("o_ld", C.c_int64),
+        ("residual", C.c_void_p), ("r_ld", C.c_int64),
+    ]
+
+
 class Ptr8(C.Structure):
     _fields_ = [("p", C.c_void_p * 8)]
 
@@ -87,6 +99,7 @@ SYMBOLS = {
     "d2r_launch_count": (C.c_int64, []),
     "d2r_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "d2r_gemm_set_profile": (C.c_int, [_vp]),
+    "d2r_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "d2r_softmax_fwd": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i32, _f, _vp]),
     "d2r_softmax_bwd": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i32, _f, _vp]),
     "d2r_pool_mean": (C.c_int, [Ptr8, _i32, _i32, _i64, _i64, _i64, _vp, _vp]),

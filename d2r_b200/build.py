@@ -18,8 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libd2r_b200.so")
-SOURCES = ["c_api.cu", "gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "router.cu", "aggregate.cu", "saf.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", "gemm_tc_epilogue.cuh", "gemm_tc2.cuh", os.path.join("..", "..", "include", "d2r_b200.h")]
+SOURCES = ["c_api.cu", "gemm_tc.cu", "attn_fused.cu", "gemm_simt.cu", "elementwise.cu", "router.cu", "aggregate.cu", "saf.cu"]
+HEADERS = ["common.cuh", "ptx.cuh", "gemm_tc_epilogue.cuh", "gemm_tc2.cuh", "tc_epi_common.cuh", "tc_host.cuh", os.path.join("..", "..", "include", "d2r_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -31,12 +31,17 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _flags():
+    """NVCC_FLAGS plus optional extra flags from the environment (D2R_NVCC_EXTRA, e.g. '-DD2R_MBAR_SPIN_LOG2=22')."""
+    return NVCC_FLAGS + os.environ.get("D2R_NVCC_EXTRA", "").split()
+
+
 def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in paths:
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -47,7 +52,7 @@ def _compile_one(nvcc: str, src: str, verbose: bool) -> str:
     dig = _digest(deps)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj
-    cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc] + _flags() + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -1,0 +1,462 @@
+// Fused attention forward for the cells of the routed stack: ONE kernel computes
+//
+//     P = softmax_row(alpha * Q K^T)        (kept in bf16, also written out for the backward)
+//     O = P V  (+ residual)                 or, for the alignment cell,  d = residual - P V,  O2 = d,  O = d * d
+//
+// for every (sample, head, 128-row query tile) "unit".  The score matrix lives in TMEM only and the probabilities
+// go from registers straight into the 128B-swizzled shared-memory tile that the second tcgen05.mma reads as its A
+// operand -- the composed path (models/SelfAttention.py:33-39, models/XModules.py:300-310, models/Cells.py:244-246
+// as two d2r_gemm launches) wrote P to HBM and read it back, and every launch drained and refilled the GPU.
+//
+// Shapes served (bf16 only): keys Lc <= 128 (one N tile: a whole score row is in one accumulator), any Lq
+// (tiles of 128 rows), head dim 48 (16-head self-attention, SelfAttention.py:27-42) or a multiple of 64 such as 768
+// (the single-head cross-modal attentions).  Operands are addressed like d2r_gemm's head-strided batches:
+// X[b, row, h * hd + col] with a row stride and (rows * row stride) per sample.
+//
+// Warp roles (320 threads, one CTA per SM, persistent over units u = blockIdx.x, += gridDim.x):
+//   warp 0      TMA producer: per unit the Q / K k-blocks of phase 1, then the V tiles of phase 2, through one ring
+//   warp 1      MMA issuer:   S(u+1) is issued BEFORE P V(u), so the softmax of unit u overlaps the next unit's
+//                             score product (two S accumulators, two P tiles, two O accumulators: 512 TMEM columns)
+//   warps 2..9  softmax + output epilogue (warp pair (q, half) shares TMEM lane quarter q, half = column half)
+// Barriers: full/empty[stage] (TMA <-> MMA), s_full/s_free[2] (MMA <-> softmax), p_ready[2] (softmax -> MMA),
+//           o_full/o_empty[2] (MMA <-> output epilogue).
+#include <cuda.h>
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <type_traits>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace d2r {
+namespace {
+
+#include "tc_host.cuh"
+#include "tc_epi_common.cuh"
+
+constexpr int kQTile = 128 * 64 * 2;    // one [128 x 64] bf16 K-major operand block = 16 KB
+constexpr int kAtom = 64 * 64 * 2;      // one [64 x 64] bf16 swizzle atom = 8 KB
+constexpr uint32_t kColS = 0, kColO = 256;   // TMEM: S0 | S1 | O0 | O1, 128 fp32 columns each
+
+template <int BNS>
+struct AfCfg {
+  static constexpr int STAGE_BYTES = kQTile + BNS * 128;            // Q k-block + K k-block (24 / 32 KB)
+  static constexpr int STAGES = BNS == 64 ? 6 : 4;
+  static constexpr int P_BYTES = (BNS / 64) * kQTile;               // one P tile [128 x BNS] bf16
+  static constexpr int STORE_BYTES = 8 * 2048;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int XCH_BYTES = 8 * 128 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * P_BYTES + STORE_BYTES + BAR_BYTES + XCH_BYTES + 1024;
+};
+
+struct AfParams {
+  int Lq, Lc, hd, heads, q_tiles, units;
+  int nkb;         // k-blocks of the score product (ceil(hd / 64))
+  int ksteps2;     // UMMA K steps (16 keys each) of the P V product that hold valid keys
+  int nt, n_tiles; // output tile width (64 | 128 columns of the head dim) and count
+  float sc;        // alpha * log2(e)
+  int mode;        // 0: O = P V (+ residual);  1: d = residual - P V, O2 = d, O = d * d
+  const __nv_bfloat16* residual;
+  long long r_ld, r_sb, r_sh;   // residual: row stride, sample stride, head stride (elements)
+};
+
+struct Unit {
+  int b, h, qt;
+};
+__device__ __forceinline__ Unit decode_unit(const AfParams& p, int u) {
+  Unit x;
+  x.qt = u % p.q_tiles;
+  const int bh = u / p.q_tiles;
+  x.h = bh % p.heads;
+  x.b = bh / p.heads;
+  return x;
+}
+
+template <int BNS>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const AfParams p) {
+  using Cfg = AfCfg<BNS>;
+  constexpr int KCB = BNS / 64;        // 64-key blocks of the P V product
+  constexpr int NCH = BNS / 32;        // 32-column chunks of a score row
+  constexpr int CPW = NCH / 2;         // chunks per warp of a pair
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* pbuf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;            // 2 x P_BYTES, 1024-aligned
+  uint8_t* store_stage = pbuf + 2 * Cfg::P_BYTES;                   // [8][2048]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* s_full = empty_bar + Cfg::STAGES;
+  uint64_t* s_free = s_full + 2;
+  uint64_t* p_ready = s_free + 2;
+  uint64_t* o_full = p_ready + 2;
+  uint64_t* o_empty = o_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  float* xch = reinterpret_cast<float*>(store_stage + Cfg::STORE_BYTES + Cfg::BAR_BYTES);   // [8][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmP);
+    tma_prefetch_desc(&tmO);
+    if (p.mode == 1) tma_prefetch_desc(&tmO2);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&s_full[a], 1);
+      mbar_init(&s_free[a], 8);
+      mbar_init(&p_ready[a], 8);
+      mbar_init(&o_full[a], 1);
+      mbar_init(&o_empty[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int n_mine = p.units > (int)blockIdx.x ? (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto load_qk = [&](int i) {
+        const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_4d(sa, &tmQ, &full_bar[stage], kb * 64, u.qt * 128, u.h, u.b);
+          tma_load_4d(sa + kQTile, &tmK, &full_bar[stage], kb * 64, 0, u.h, u.b);
+          advance();
+        }
+      };
+      auto load_v = [&](int i) {
+        const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+        const int atoms = p.nt / 64;
+        for (int t = 0; t < p.n_tiles; ++t) {
+          for (int kc = 0; kc < KCB; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], atoms * kAtom);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            for (int a = 0; a < atoms; ++a)
+              tma_load_4d(sa + a * kAtom, &tmV, &full_bar[stage], t * p.nt + 64 * a, kc * 64, u.h, u.b);
+            advance();
+          }
+        }
+      };
+      if (n_mine > 0) load_qk(0);
+      for (int i = 0; i < n_mine; ++i) {
+        if (i + 1 < n_mine) load_qk(i + 1);
+        load_v(i);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BNS, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, p.nt, 0, 1);      // A = P (K-major), B = V (MN-major)
+      int stage = 0;
+      uint32_t phase = 0;
+      int oc = 0;                                                      // output tiles issued so far
+      auto advance = [&]() {
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto issue_s = [&](int i) {
+        const int sb = i & 1;
+        mbar_wait(&s_free[sb], (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + kColS + static_cast<uint32_t>(sb * 128);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sk = sa + kQTile;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024),
+                      idesc_s, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          advance();
+        }
+        umma_commit(&s_full[sb]);
+      };
+      auto issue_pv = [&](int i) {
+        const int sb = i & 1;
+        mbar_wait(&p_ready[sb], static_cast<uint32_t>(i >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(pbuf + sb * Cfg::P_BYTES);
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int ob = oc & 1;
+          mbar_wait(&o_empty[ob], (static_cast<uint32_t>(oc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kColO + static_cast<uint32_t>(ob * 128);
+          for (int kc = 0; kc < KCB; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sv = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (kc * 4 + k < p.ksteps2)
+                umma_bf16(d_tmem, make_smem_desc_sw128(pa + kc * kQTile + k * 32, 16, 1024),
+                          make_smem_desc_sw128(sv + k * 2048, kAtom, 1024), idesc_o, (kc > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            advance();
+          }
+          umma_commit(&o_full[ob]);
+          ++oc;
+        }
+      };
+      if (n_mine > 0) issue_s(0);
+      for (int i = 0; i < n_mine; ++i) {
+        if (i + 1 < n_mine) issue_s(i + 1);
+        issue_pv(i);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- softmax + output epilogue
+    const int q = warp & 3;                     // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;           // which half of the columns
+    const int ew = warp - 2;
+    uint8_t* stg = store_stage + ew * 2048;
+    float* xch_mine = xch + ew * 128;
+    const float* xch_peer = xch + (half == 0 ? ew + 4 : ew - 4) * 128;
+    const int r = q * 32 + lane;                // row of the unit's 128-row tile
+    int oc = 0;
+    for (int i = 0; i < n_mine; ++i) {
+      const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+      const int sb = i & 1;
+      uint8_t* pb = pbuf + sb * Cfg::P_BYTES;
+      // ---- softmax of this warp pair's 32 rows; this warp owns CPW chunks of 32 columns
+      mbar_wait(&s_full[sb], static_cast<uint32_t>(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + kColS + static_cast<uint32_t>(sb * 128) + (static_cast<uint32_t>(q * 32) << 16);
+      float e[CPW * 32];
+      float ml = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = half * CPW + cc;
+        uint32_t ra[32];
+        tmem_ld32(ts + c * 32, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = (c * 32 + j < p.Lc) ? p.sc * __uint_as_float(ra[j]) : -INFINITY;
+          e[cc * 32 + j] = x;
+          ml = fmaxf(ml, x);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[sb]);  // the score accumulator may be overwritten (unit i + 2)
+      const float ms = ml == -INFINITY ? 0.f : ml;
+      float sl = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPW * 32; ++j) {
+        e[j] = ex2_ftz(e[j] - ms);
+        sl += e[j];
+      }
+      *reinterpret_cast<float2*>(xch_mine + lane * 2) = make_float2(ml, sl);
+      // the bulk stores that read this P tile two units ago were issued by this lane: drained before anyone rewrites
+      if (half == 0 && lane == 0) bulk_wait_read0();
+      pair_barrier(q);
+      const float2 pp = *reinterpret_cast<const float2*>(xch_peer + lane * 2);
+      const float mx = fmaxf(ml, pp.x);
+      const float mine = ex2_ftz(ml - mx);
+      const float f = mine / (sl * mine + pp.y * ex2_ftz(pp.x - mx));
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = half * CPW + cc;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t8[j] = e[cc * 32 + g * 8 + j] * f;
+          const int col0 = c * 32 + g * 8;
+          const int unit16 = (col0 & 63) >> 3;
+          *reinterpret_cast<uint4*>(pb + (col0 >> 6) * kQTile + r * 128 + ((unit16 ^ (r & 7)) << 4)) = pack8_bf16(t8);
+        }
+      }
+      fence_proxy_async();                      // generic-proxy writes of P -> visible to tcgen05.mma / TMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[sb]);
+      pair_barrier(q);                          // both halves of this quarter's rows are in shared memory
+      if (half == 0 && lane == 0) {
+#pragma unroll
+        for (int a = 0; a < KCB; ++a)
+          tma_store_4d(&tmP, pb + a * kQTile + q * 32 * 128, a * 64, u.qt * 128 + q * 32, u.h, u.b);
+        bulk_commit();
+      }
+      // ---- output tiles of this unit
+      const int row0 = u.qt * 128 + q * 32;
+      const bool row_ok = row0 + lane < p.Lq;
+      const __nv_bfloat16* rrow = nullptr;
+      if (p.residual)
+        rrow = p.residual + static_cast<long long>(u.b) * p.r_sb + static_cast<long long>(u.h) * p.r_sh +
+               static_cast<long long>(row0 + lane) * p.r_ld;
+      const int nco = p.nt >> 5;                // 32-column chunks per output tile (2 | 4)
+      const int cpo = nco >> 1;
+      for (int t = 0; t < p.n_tiles; ++t) {
+        const int ob = oc & 1;
+        mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
+        tc_fence_after();
+        for (int cc = 0; cc < cpo; ++cc) {
+          const int c = half * cpo + cc;
+          const int col0 = t * p.nt + c * 32;   // column inside the head
+          if (col0 >= p.hd) continue;
+          uint32_t ra[32];
+          float v[32], d[32];
+          tmem_ld32(tmem_base + kColO + static_cast<uint32_t>(ob * 128) + (static_cast<uint32_t>(q * 32) << 16) + c * 32, ra);
+          float res[32];
+          if (rrow != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float t8[8];
+              const int nvalid = row_ok ? max(0, min(8, p.hd - col0 - g * 8)) : 0;
+              ld_group(rrow + col0 + g * 8, t8, nvalid);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) res[g * 8 + j] = t8[j];
+            }
+          }
+          tmem_ld_wait();
+          if (p.mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              d[j] = res[j] - __uint_as_float(ra[j]);
+              v[j] = d[j] * d[j];
+            }
+            tma_store_row32<__nv_bfloat16>(&tmO2, stg, lane, d, col0, row0, u.h, u.b);
+          } else if (rrow != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + res[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+          }
+          tma_store_row32<__nv_bfloat16>(&tmO, stg, lane, v, col0, row0, u.h, u.b);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[ob]);
+        ++oc;
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BNS>
+int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmP,
+                    const CUtensorMap& tmO, const CUtensorMap& tmO2, const AfParams& p, cudaStream_t stream) {
+  using Cfg = AfCfg<BNS>;
+  auto kern = attn_fwd_kernel<BNS>;
+  static std::atomic<int> attr_set[kMaxDevices];
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev].store(1, std::memory_order_release);
+  }
+  const int grid = p.units < num_sms() ? p.units : num_sms();
+  D2R_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), Cfg::SMEM_BYTES, stream, tmQ, tmK, tmV, tmP, tmO, tmO2, p));
+  count_launch();
+  return check_launch("attn_fwd_kernel");
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int d2r_attn_fwd(const d2r_attn_args* a, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(a != nullptr && a->q && a->k && a->v && a->p && a->out, "attn_fwd: null argument");
+  D2R_CHECK_ARG(a->B > 0 && a->heads > 0 && a->Lq > 0 && a->Lc > 0 && a->hd > 0, "attn_fwd: empty problem");
+  D2R_CHECK_ARG(a->Lc <= 128, "attn_fwd: at most 128 keys (got %d): use the composed d2r_gemm path", a->Lc);
+  D2R_CHECK_ARG(a->hd % 16 == 0 && (a->hd <= 64 || a->hd % 64 == 0), "attn_fwd: head dim %d unsupported", a->hd);
+  D2R_CHECK_ARG(a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->p_ld % 8 == 0 && a->o_ld % 8 == 0 &&
+                    a->hd % 8 == 0 && a->p_ld >= a->Lc,
+                "attn_fwd: leading dimensions must be multiples of 8 elements (TMA 16-byte rule)");
+  D2R_CHECK_ARG(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->p) && aligned16(a->out),
+                "attn_fwd: operands must be 16-byte aligned");
+  D2R_CHECK_ARG(a->mode == 0 || (a->mode == 1 && a->residual && a->out2 && aligned16(a->out2)),
+                "attn_fwd: mode 1 (squared difference) needs residual and out2");
+  D2R_CHECK_ARG(!a->residual || (a->r_ld % 8 == 0 && aligned16(a->residual)), "attn_fwd: residual layout");
+  const int bns = a->Lc <= 64 ? 64 : 128;
+  AfParams p;
+  p.Lq = a->Lq; p.Lc = a->Lc; p.hd = a->hd; p.heads = a->heads;
+  p.q_tiles = (a->Lq + 127) / 128;
+  p.units = a->B * a->heads * p.q_tiles;
+  p.nkb = (a->hd + 63) / 64;
+  p.ksteps2 = (a->Lc + 15) / 16;
+  p.nt = a->hd <= 64 ? 64 : 128;
+  p.n_tiles = (a->hd + p.nt - 1) / p.nt;
+  p.sc = a->alpha * 1.4426950408889634f;
+  p.mode = a->mode;
+  p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  p.r_ld = a->r_ld; p.r_sb = (long long)a->Lq * a->r_ld; p.r_sh = a->hd;
+  const long long H = a->heads, B = a->B;
+  CUtensorMap tmQ, tmK, tmV, tmP, tmO, tmO2;
+  memset(&tmO2, 0, sizeof(tmO2));
+  int rc;
+  // operands: {head dim, rows, heads, samples}; head stride = hd elements, sample stride = rows * ld
+  if ((rc = encode_map(&tmQ, a->q, 2, a->hd, a->Lq, H, B, a->q_ld, a->hd, (long long)a->Lq * a->q_ld, 64, 128,
+                       CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_map(&tmK, a->k, 2, a->hd, a->Lc, H, B, a->k_ld, a->hd, (long long)a->Lc * a->k_ld, 64, bns,
+                       CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_map(&tmV, a->v, 2, a->hd, a->Lc, H, B, a->v_ld, a->hd, (long long)a->Lc * a->v_ld, 64, 64,
+                       CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  // P [B, heads, Lq, p_ld]: stored straight from the swizzled shared-memory tile, 32 rows x 64 columns per store
+  if ((rc = encode_map(&tmP, a->p, 2, a->Lc, a->Lq, H, B, a->p_ld, (long long)a->Lq * a->p_ld,
+                       H * a->Lq * a->p_ld, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_map(&tmO, a->out, 2, a->hd, a->Lq, H, B, a->o_ld, a->hd, (long long)a->Lq * a->o_ld, 32, 32,
+                       CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if (a->mode == 1 &&
+      (rc = encode_map(&tmO2, a->out2, 2, a->hd, a->Lq, H, B, a->o_ld, a->hd, (long long)a->Lq * a->o_ld, 32, 32,
+                       CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if (bns == 64) return launch_attn_fwd<64>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
+  return launch_attn_fwd<128>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
+}
+
+}  // extern "C"
+}  // namespace d2r

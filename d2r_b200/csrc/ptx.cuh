@@ -52,6 +52,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (kernel fails with an error) instead of hanging the GPU.  The bound is
 // generous -- 2^28 polls of a try_wait that itself suspends the thread for a while, i.e. minutes, far beyond any
 // time-slice another context can take from this one -- and -DD2R_NO_TRAP removes it altogether.
+#ifndef D2R_MBAR_SPIN_LOG2
+#define D2R_MBAR_SPIN_LOG2 28     // bring-up builds pass -DD2R_MBAR_SPIN_LOG2=22 (D2R_NVCC_EXTRA) to fail within a second
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifdef D2R_NO_TRAP
   while (!mbar_try_wait(bar, parity)) {
@@ -59,7 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #else
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
+    if (++spins > (1u << D2R_MBAR_SPIN_LOG2)) {
       __trap();
     }
   }

@@ -87,55 +87,84 @@ __global__ void __launch_bounds__(1024) saf_stats_kernel(const float* __restrict
 }
 
 // block per sample: a = l1norm(sigmoid(bn(logit))); saf = sum_l a_l S_l; out = l2norm(saf)
+// kOutThreads = 3 row phases x 96 column groups of 8 (16-byte loads, four rows in flight per thread); round 1 read
+// the [L+1, D] slab with scalar 2-byte loads, one row at a time (0.11 of the HBM peak).
+constexpr int kOutGroups = 96;
+constexpr int kOutPhases = 3;
+constexpr int kOutThreads = kOutGroups * kOutPhases;
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads) saf_out_kernel(const T* __restrict__ sg, const T* __restrict__ sl,
-                                                           const float* __restrict__ logits,
-                                                           const float* __restrict__ stats,
-                                                           const float* __restrict__ bn_w,
-                                                           const float* __restrict__ bn_b, long long L, long long D,
-                                                           float* __restrict__ attn, float* __restrict__ rnorm,
-                                                           float* __restrict__ out) {
-  extern __shared__ float s_attn[];   // L+1
-  __shared__ float sm[8];
+__global__ void __launch_bounds__(kOutThreads) saf_out_kernel(const T* __restrict__ sg, const T* __restrict__ sl,
+                                                              const float* __restrict__ logits,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ bn_w,
+                                                              const float* __restrict__ bn_b, long long L, long long D,
+                                                              float* __restrict__ attn, float* __restrict__ rnorm,
+                                                              float* __restrict__ out) {
+  extern __shared__ float s_dyn[];    // attn [L+1] (padded to a multiple of 4), then partial sums [kOutPhases][D]
+  float* s_attn = s_dyn;
+  float* s_part = s_dyn + ((L + 1 + 3) / 4) * 4;
+  __shared__ float sm[32];
   const long long b = blockIdx.x;
   const float mean = stats[0], invstd = stats[1], gw = bn_w[0], gb = bn_b[0];
   float part = 0.f;
-  for (long long l = threadIdx.x; l <= L; l += kThreads) {
+  for (long long l = threadIdx.x; l <= L; l += kOutThreads) {
     const float y = (logits[b * (L + 1) + l] - mean) * invstd * gw + gb;
-    const float s = 1.f / (1.f + __expf(-y));
-    s_attn[l] = s;
-    part += s;
+    const float sg_ = 1.f / (1.f + __expf(-y));
+    s_attn[l] = sg_;
+    part += sg_;
   }
   const float tot = block_sum(part, sm);
   const float inv = 1.f / (tot + 1e-8f);
-  for (long long l = threadIdx.x; l <= L; l += kThreads) {
+  for (long long l = threadIdx.x; l <= L; l += kOutThreads) {
     const float a = s_attn[l] * inv;
     s_attn[l] = a;
     attn[b * (L + 1) + l] = a;
   }
   __syncthreads();
-  // each thread owns columns c = tid*4 + k*1024
+  const int rp = threadIdx.x / kOutGroups;
+  const long long G = D / 8;
+  for (long long g = threadIdx.x % kOutGroups; g < G; g += kOutGroups) {
+    const long long c = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long l = rp; l <= L; l += 4 * kOutPhases) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long lu = l + u * kOutPhases;
+        if (lu <= L) {
+          load8(saf_row(sg, sl, b, lu, L, D) + c, v[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long lu = l + u * kOutPhases;
+        const float a = lu <= L ? s_attn[lu] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, v[u][j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[rp * D + c + j] = acc[j];
+  }
+  __syncthreads();
   float ss = 0.f;
-  for (long long c = threadIdx.x * 4; c < D; c += kThreads * 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long l = 0; l <= L; ++l) {
-      const T* s = saf_row(sg, sl, b, l, L, D) + c;
-      const float a = s_attn[l];
+  for (long long c = threadIdx.x; c < D; c += kOutThreads) {
+    float a = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(a, Elem<T>::ld(s + q), acc[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      out[b * D + c + q] = acc[q];
-      ss += acc[q] * acc[q];
-    }
+    for (int r = 0; r < kOutPhases; ++r) a += s_part[r * D + c];
+    s_part[c] = a;                    // (phase 0's slot of column c is only read by this thread)
+    ss += a * a;
   }
   ss = block_sum(ss, sm);
   const float r = 1.f / (sqrtf(ss) + 1e-8f);
   if (threadIdx.x == 0) rnorm[b] = r;
-  for (long long c = threadIdx.x * 4; c < D; c += kThreads * 4)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) out[b * D + c + q] *= r;
+  for (long long c = threadIdx.x; c < D; c += kOutThreads) out[b * D + c] = s_part[c] * r;
 }
 
 // ---------------------------------------------------------------- backward
@@ -168,17 +197,35 @@ __global__ void __launch_bounds__(kThreads) saf_bwd_a_kernel(const T* __restrict
     d_saf[b * D + c] = v;
   }
   __syncthreads();
-  for (long long l = warp; l <= L; l += kThreads / 32) {
-    const T* s = saf_row(sg, sl, b, l, L, D);
-    float acc = 0.f;
+  // four rows per warp and iteration: their loads are all in flight before the first dot product starts
+  for (long long l = warp; l <= L; l += 4 * (kThreads / 32)) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long c = lane * 8; c < D; c += 256) {
-      float v[8];
-      load8(s + c, v);
+      float v[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc = fmaf(v[j], s_dsaf[c + j], acc);
+      for (int u = 0; u < 4; ++u) {
+        const long long lu = l + u * (kThreads / 32);
+        if (lu <= L) {
+          load8(saf_row(sg, sl, b, lu, L, D) + c, v[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = s_dsaf[c + j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[u] = fmaf(v[u][j], g[j], acc[u]);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) s_da[l] = acc;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float a = warp_sum(acc[u]);
+      const long long lu = l + u * (kThreads / 32);
+      if (lane == 0 && lu <= L) s_da[lu] = a;
+    }
   }
   __syncthreads();
   // a = s / (T + eps):  d_s = (d_a - sum_l d_a a) / (T + eps);   T + eps = s / a (any l)
@@ -303,15 +350,15 @@ int d2r_saf_fwd(const d2r_saf_args* a, void* stream) {
   D2R_CHECK_ARG(a && a->B > 0 && a->L > 0 && a->D % 8 == 0, "saf: bad shape");
   const long long N = a->B * (a->L + 1);
   const unsigned grid_rows = (unsigned)((N + 7) / 8);
-  const size_t sh = sizeof(float) * (size_t)(a->L + 1);
-  D2R_CHECK_ARG(sh <= 40 * 1024, "saf: L too large");
+  const size_t sh = sizeof(float) * (size_t)(((a->L + 1 + 3) / 4) * 4 + kOutPhases * a->D);
+  D2R_CHECK_ARG(sh <= 40 * 1024, "saf: L + 3 D too large");
   D2R_DISPATCH_DTYPE(a->dtype, T,
                      saf_logit_kernel<T><<<grid_rows, kThreads, 0, st>>>((const T*)a->sg, (const T*)a->sl, a->w, a->bias,
                                                                          a->B, a->L, a->D, a->logits));
   saf_stats_kernel<<<1, 1024, 0, st>>>(a->logits, N, a->training, a->running_mean, a->running_var,
                                        (long long*)a->num_batches_tracked, a->stats);
   D2R_DISPATCH_DTYPE(a->dtype, T,
-                     saf_out_kernel<T><<<(unsigned)a->B, kThreads, sh, st>>>((const T*)a->sg, (const T*)a->sl, a->logits,
+                     saf_out_kernel<T><<<(unsigned)a->B, kOutThreads, sh, st>>>((const T*)a->sg, (const T*)a->sl, a->logits,
                                                                              a->stats, a->bn_w, a->bn_b, a->L, a->D,
                                                                              a->attn, a->rnorm, a->out));
   count_launch(3);

@@ -102,6 +102,34 @@ def gemm(a: Tensor, b: Tensor, c: Tensor, *, m: int, n: int, k: int, lda: int, l
     return c
 
 
+def attn_fused_supported(dtype: torch.dtype, Lc: int, hd: int) -> bool:
+    """Shapes the fused attention kernel serves (see d2r_attn_fwd in include/d2r_b200.h)."""
+    return dtype == torch.bfloat16 and Lc <= 128 and hd % 16 == 0 and (hd <= 64 or hd % 64 == 0)
+
+
+def attn_fused_fwd(q: Tensor, q_ld: int, k: Tensor, k_ld: int, v: Tensor, v_ld: int, *, B: int, Lq: int, Lc: int,
+                   D: int, heads: int, alpha: float, p_ld: int, residual: Optional[Tensor] = None, mode: int = 0,
+                   out2: Optional[Tensor] = None):
+    """-> (out [B,Lq,D], P [B,heads,Lq,p_ld], out2 | None).  q/k/v may be column slices of wider buffers
+    (row strides q_ld / k_ld / v_ld); residual is a contiguous [B,Lq,D] tensor; mode 1 = squared difference
+    (out2 = residual - attention, out = out2^2), written into ``out2`` when given."""
+    L.require_cuda(q, k, v, residual, out2)
+    out = torch.empty(B, Lq, D, device=q.device, dtype=torch.bfloat16)
+    if mode == 1 and out2 is None:
+        out2 = torch.empty_like(out)
+    P = torch.empty(B, heads, Lq, p_ld, device=q.device, dtype=torch.bfloat16)
+    a = L.AttnArgs()
+    a.B, a.heads, a.Lq, a.Lc, a.hd = B, heads, Lq, Lc, D // heads
+    a.mode, a.alpha = mode, alpha
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.q_ld, a.k_ld, a.v_ld = q_ld, k_ld, v_ld
+    a.p, a.p_ld = P.data_ptr(), p_ld
+    a.out, a.out2, a.o_ld = out.data_ptr(), L.ptr(out2), D
+    a.residual, a.r_ld = L.ptr(residual), D
+    L.check(L.lib.d2r_attn_fwd(C.byref(a), L.stream()), "attn_fwd")
+    return out, P, out2
+
+
 def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int = L.ACT_NONE,
            residual: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None,
            out: Optional[Tensor] = None, epilogue: int = L.EPI_STD, c2: Optional[Tensor] = None,

@@ -34,6 +34,7 @@ from . import lanes as LN
 Tensor = torch.Tensor
 CELLS6 = ("ric", "glac", "imrc", "cmrc", "crcmc", "gesc")   # emb_lst order, DynamicInteraction.py:41-48
 CMA_TEMPERATURE = 100.0
+FUSED_ATTN = True      # attention forward as ONE kernel (d2r_attn_fwd) where the shape allows; False: two d2r_gemm launches
 
 
 def pad8(n: int) -> int:
@@ -268,6 +269,11 @@ def attn_fwd(q: Tensor, q_ld: int, k: Tensor, k_ld: int, v: Tensor, v_ld: int, B
     dh = D // heads
     Lcp = pad8(Lc)
     dev = q.device
+    if FUSED_ATTN and K.attn_fused_supported(cd, Lc, dh):
+        # one kernel: scores in TMEM, probabilities handed to the second MMA through shared memory
+        out, P, _ = K.attn_fused_fwd(q, q_ld, k, k_ld, v, v_ld, B=B, Lq=Lq, Lc=Lc, D=D, heads=heads, alpha=alpha,
+                                     p_ld=Lcp, residual=residual, mode=1 if epilogue == L.EPI_SQDIFF else 0, out2=c2)
+        return out, P
     if _fused_softmax(cd, Lc):
         # scores stay in TMEM: the GEMM's epilogue normalises the row and writes P directly
         P = torch.empty(B, heads, Lq, Lcp, device=dev, dtype=cd)

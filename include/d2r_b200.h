@@ -97,6 +97,34 @@ int d2r_gemm(const d2r_gemm_args* args, void* stream);
  * and one epilogue warp waiting for an accumulator.  Pass NULL to switch it off (the default). */
 int d2r_gemm_set_profile(int64_t* records);
 
+/* ---- (b) fused attention (bf16 tensor-core path) ------------------------------------------
+ * One kernel for  P = softmax_row(alpha * Q K^T),  O = P V (+ residual)  -- or, for the alignment cell
+ * (Cells.py:149), d = residual - P V, out2 = d, out = d * d -- per (sample, head): the scores stay in TMEM,
+ * the probabilities go from registers into the shared-memory operand of the second tcgen05.mma and are also
+ * written to `p` for the backward.  Replaces the pair of d2r_gemm launches (EPI_SOFTMAX, then P V) for
+ * SelfAttention.py:33-39 (16 heads, head dim 48), XModules.py:300-310 / Refinement.py:105-115 (single head,
+ * dim 768, alpha = 100/sqrt(768)) and Cells.py:244-246 (single head, unscaled).
+ * Operands are bf16, addressed X[b, row, h*hd + col] with row stride x_ld and rows*x_ld per sample.
+ * Limits: Lc <= 128, hd = 16..64 or a multiple of 64, every ld a multiple of 8, 16-byte aligned pointers. */
+typedef struct d2r_attn_args {
+  int32_t B, heads, Lq, Lc, hd;
+  int32_t mode;          /* 0: out = P V (+ residual);  1: squared difference (needs residual and out2) */
+  float alpha;           /* softmax(alpha * q.k) */
+  int32_t reserved0;
+  const void* q;         /* [B, Lq, heads*hd] */
+  const void* k;         /* [B, Lc, heads*hd] */
+  const void* v;         /* [B, Lc, heads*hd] */
+  int64_t q_ld, k_ld, v_ld;
+  void* p;               /* written: [B, heads, Lq, p_ld] probabilities, p_ld >= Lc */
+  int64_t p_ld;
+  void* out;             /* written: [B, Lq, heads*hd] with row stride o_ld */
+  void* out2;            /* written in mode 1, same layout as out */
+  int64_t o_ld;
+  const void* residual;  /* optional, [B, Lq, heads*hd] with row stride r_ld */
+  int64_t r_ld;
+} d2r_attn_args;
+int d2r_attn_fwd(const d2r_attn_args* a, void* stream);
+
 /* Row softmax over the last dim, optional scale: y = softmax(scale * x).  x fp32 or bf16
  * [rows, cols] with row stride ldx; y bf16 or fp32 with row stride ldy.
  * SelfAttention.py:33-37, XModules.py:306-309, Cells.py:244-245.  */
