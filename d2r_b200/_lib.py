@@ -50,6 +50,17 @@ class AttnArgs(C.Structure):
     ]
 
 
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("heads", C.c_int32), ("Lq", C.c_int32), ("Lc", C.c_int32), ("hd", C.c_int32),
+        ("reserved0", C.c_int32), ("alpha", C.c_float), ("sign", C.c_float),
+        ("d_out", C.c_void_p), ("p", C.c_void_p), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("do_ld", C.c_int64), ("p_ld", C.c_int64), ("q_ld", C.c_int64), ("k_ld", C.c_int64), ("v_ld", C.c_int64),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("dq_ld", C.c_int64), ("dk_ld", C.c_int64), ("dv_ld", C.c_int64),
+    ]
+
+
 class Ptr8(C.Structure):
     _fields_ = [("p", C.c_void_p * 8)]
 
@@ -100,6 +111,7 @@ SYMBOLS = {
     "d2r_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "d2r_gemm_set_profile": (C.c_int, [_vp]),
     "d2r_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "d2r_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _vp]),
     "d2r_softmax_fwd": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i32, _f, _vp]),
     "d2r_softmax_bwd": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i32, _f, _vp]),
     "d2r_pool_mean": (C.c_int, [Ptr8, _i32, _i32, _i64, _i64, _i64, _vp, _vp]),

@@ -402,6 +402,358 @@ int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtens
   return check_launch("attn_fwd_kernel");
 }
 
+
+// ===================================================================== backward
+// One kernel per attention for Lq <= 128, Lc <= 128 (one tile per (sample, head)):
+//
+//   dP  = sign * dO V^T                      scores accumulator (TMEM), k = head dim
+//   dS  = alpha * P o (dP - rowsum(dP o P))  registers -> bf16 tile in shared memory ([q, c], 128B swizzle);
+//                                            P (read once from HBM) goes into a second tile
+//   dV  = sign * P^T dO      A = P tile read MN-major,  B = dO streamed again as [q rows, n columns]
+//   dQ  = dS K               A = dS tile read K-major,  B = K streamed
+//   dK  = dS^T Q             A = dS tile read MN-major, B = Q streamed
+//
+// The composed path ran four d2r_gemm launches (models/SelfAttention.py:33-39 backward etc.), each re-reading
+// its [B*Lq, D] operands from HBM and round-tripping dS.  Same warp roles and barrier scheme as the forward;
+// the output products share two TMEM accumulators, one tile of NT head-dim columns at a time.
+struct AbParams {
+  int Lq, Lc, hd, heads, units;
+  int nkb;            // k-blocks of the dP product (ceil(hd / 64))
+  int ksteps_q;       // valid UMMA K steps when the contraction runs over queries (ceil(Lq / 16))
+  int ksteps_c;       // ... over keys (ceil(Lc / 16))
+  int nt, n_tiles;    // output tile width (64 | 128) and tiles per output
+  float alpha, sign;
+  const __nv_bfloat16* P;
+  long long p_ld;
+};
+
+template <int BNS>
+struct AbCfg {
+  static constexpr int STAGE_BYTES = 2 * kQTile;                     // 32 KB: dO block + V block, or one B tile
+  static constexpr int STAGES = 4;
+  static constexpr int TILE_BYTES = 2 * kQTile;                      // [128 x 128] bf16, two 64-column atoms
+  static constexpr int STORE_BYTES = 8 * 2048;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int XCH_BYTES = 8 * 128 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TILE_BYTES + STORE_BYTES + BAR_BYTES + XCH_BYTES + 1024;
+};
+
+template <int BNS>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmV,
+                const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
+                const __grid_constant__ CUtensorMap tmDV, const __grid_constant__ CUtensorMap tmDQ,
+                const __grid_constant__ CUtensorMap tmDK, const AbParams p) {
+  using Cfg = AbCfg<BNS>;
+  constexpr int NCH = BNS / 32;
+  constexpr int CPW = NCH / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* ptile = smem + Cfg::STAGES * Cfg::STAGE_BYTES;           // P  [128 q x 128 c]
+  uint8_t* dstile = ptile + Cfg::TILE_BYTES;                        // dS [128 q x 128 c]
+  uint8_t* store_stage = dstile + Cfg::TILE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* s_full = empty_bar + Cfg::STAGES;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* ds_ready = s_free + 1;
+  uint64_t* o_full = ds_ready + 1;
+  uint64_t* o_empty = o_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  float* xch = reinterpret_cast<float*>(store_stage + Cfg::STORE_BYTES + Cfg::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDV);
+    tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmDK);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 8);
+    mbar_init(ds_ready, 8);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&o_full[a], 1);
+      mbar_init(&o_empty[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // the tiles' second 64-column atom is never written when there are at most 64 keys: it must read as zero
+  for (int i = threadIdx.x; i < 2 * Cfg::TILE_BYTES / 16; i += kTcThreads)
+    reinterpret_cast<uint4*>(ptile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int n_mine = p.units > (int)blockIdx.x ? (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int atoms = p.nt / 64;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto load_dp = [&](int i) {
+        const int u = (int)blockIdx.x + i * (int)gridDim.x;
+        const int h = u % p.heads, b = u / p.heads;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kQTile + BNS * 128);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_4d(sa, &tmDO, &full_bar[stage], kb * 64, 0, h, b);
+          tma_load_4d(sa + kQTile, &tmV, &full_bar[stage], kb * 64, 0, h, b);
+          advance();
+        }
+      };
+      auto load_outs = [&](int i) {
+        const int u = (int)blockIdx.x + i * (int)gridDim.x;
+        const int h = u % p.heads, b = u / p.heads;
+        for (int o = 0; o < 3; ++o) {
+          const CUtensorMap* tm = o == 0 ? &tmDO : (o == 1 ? &tmK : &tmQ);
+          for (int t = 0; t < p.n_tiles; ++t) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], atoms * kQTile);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            for (int a = 0; a < atoms; ++a) tma_load_4d(sa + a * kQTile, tm, &full_bar[stage], t * p.nt + 64 * a, 0, h, b);
+            advance();
+          }
+        }
+      };
+      if (n_mine > 0) load_dp(0);
+      for (int i = 0; i < n_mine; ++i) {
+        load_outs(i);
+        if (i + 1 < n_mine) load_dp(i + 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_dp = make_idesc_bf16(128, BNS, 0, 0);
+      const uint32_t idesc_mn = make_idesc_bf16(128, p.nt, 1, 1);     // dV, dK: A tile read MN-major
+      const uint32_t idesc_k = make_idesc_bf16(128, p.nt, 0, 1);      // dQ: A tile read K-major
+      const uint32_t pt = smem_u32(ptile), dt = smem_u32(dstile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int oc = 0;
+      auto advance = [&]() {
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto issue_dp = [&](int i) {
+        mbar_wait(s_free, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + kColS;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sv = sa + kQTile;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sv + k * 32, 16, 1024),
+                      idesc_dp, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          advance();
+        }
+        umma_commit(s_full);
+      };
+      auto issue_outs = [&](int i) {
+        mbar_wait(ds_ready, static_cast<uint32_t>(i) & 1u);
+        tc_fence_after();
+        for (int o = 0; o < 3; ++o) {
+          const int ksteps = o == 1 ? p.ksteps_c : p.ksteps_q;
+          for (int t = 0; t < p.n_tiles; ++t) {
+            const int ob = oc & 1;
+            mbar_wait(&o_empty[ob], (static_cast<uint32_t>(oc >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + kColO + static_cast<uint32_t>(ob * 128);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            for (int k = 0; k < ksteps; ++k) {
+              // B tile: [128 contraction rows x 64-column atoms], atoms 16 KB apart, 16 rows = 2048 B per K step
+              const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kQTile, 1024);
+              uint64_t da;
+              if (o == 0) da = make_smem_desc_sw128(pt + k * 2048, kQTile, 1024);          // P^T  (M = keys)
+              else if (o == 2) da = make_smem_desc_sw128(dt + k * 2048, kQTile, 1024);     // dS^T (M = keys)
+              else da = make_smem_desc_sw128(dt + (k >> 2) * kQTile + (k & 3) * 32, 16, 1024);   // dS (M = queries)
+              umma_bf16(d_tmem, da, db, o == 1 ? idesc_k : idesc_mn, k > 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            advance();
+            umma_commit(&o_full[ob]);
+            ++oc;
+          }
+        }
+      };
+      if (n_mine > 0) issue_dp(0);
+      for (int i = 0; i < n_mine; ++i) {
+        issue_outs(i);
+        if (i + 1 < n_mine) issue_dp(i + 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- softmax backward + output epilogue
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    uint8_t* stg = store_stage + ew * 2048;
+    float* xch_mine = xch + ew * 128;
+    const float* xch_peer = xch + (half == 0 ? ew + 4 : ew - 4) * 128;
+    const int r = q * 32 + lane;
+    const bool row_ok = r < p.Lq;
+    int oc = 0;
+    for (int i = 0; i < n_mine; ++i) {
+      const int u = (int)blockIdx.x + i * (int)gridDim.x;
+      const int h = u % p.heads, b = u / p.heads;
+      const __nv_bfloat16* prow = p.P + (static_cast<long long>(u) * p.Lq + r) * p.p_ld;
+      mbar_wait(s_full, static_cast<uint32_t>(i) & 1u);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + kColS + (static_cast<uint32_t>(q * 32) << 16);
+      // pass 1: this warp's share of sum_c dP P; P is fetched once and kept packed
+      float part = 0.f;
+      uint4 pk[CPW][4];
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = half * CPW + cc;
+        uint32_t ra[32];
+        tmem_ld32(ts + c * 32, ra);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pr[8];
+          ld_group(prow + c * 32 + g * 8, pr, row_ok ? max(0, min(8, p.Lc - c * 32 - g * 8)) : 0);
+          pk[cc][g] = pack8_bf16(pr);            // exact: P is bf16 in memory
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&pk[cc][g]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(hh[j]);
+            part = fmaf(p.sign * __uint_as_float(ra[g * 8 + 2 * j]), f.x, part);
+            part = fmaf(p.sign * __uint_as_float(ra[g * 8 + 2 * j + 1]), f.y, part);
+          }
+        }
+      }
+      xch_mine[lane] = part;
+      pair_barrier(q);
+      const float tot = part + xch_peer[lane];
+      // pass 2: dS = alpha P (sign dP - total) -> shared memory, next to the P tile
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = half * CPW + cc;
+        uint32_t ra[32];
+        tmem_ld32(ts + c * 32, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&pk[cc][g]);
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(hh[j]);
+            t8[2 * j] = p.alpha * f.x * (p.sign * __uint_as_float(ra[g * 8 + 2 * j]) - tot);
+            t8[2 * j + 1] = p.alpha * f.y * (p.sign * __uint_as_float(ra[g * 8 + 2 * j + 1]) - tot);
+          }
+          const int col0 = c * 32 + g * 8;
+          const int off = (col0 >> 6) * kQTile + r * 128 + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dstile + off) = pack8_bf16(t8);
+          *reinterpret_cast<uint4*>(ptile + off) = pk[cc][g];
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_free);
+        mbar_arrive(ds_ready);
+      }
+      // ---- output tiles: dV, dQ, dK
+      for (int o = 0; o < 3; ++o) {
+        const CUtensorMap* tm = o == 0 ? &tmDV : (o == 1 ? &tmDQ : &tmDK);
+        const float scale = o == 0 ? p.sign : 1.f;
+        const int nco = p.nt >> 5, cpo = nco >> 1;
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int ob = oc & 1;
+          mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
+          tc_fence_after();
+          for (int cc = 0; cc < cpo; ++cc) {
+            const int c = half * cpo + cc;
+            const int col0 = t * p.nt + c * 32;
+            if (col0 >= p.hd) continue;
+            uint32_t ra[32];
+            float v[32];
+            tmem_ld32(tmem_base + kColO + static_cast<uint32_t>(ob * 128) + (static_cast<uint32_t>(q * 32) << 16) + c * 32, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = scale * __uint_as_float(ra[j]);
+            tma_store_row32<__nv_bfloat16>(tm, stg, lane, v, col0, q * 32, h, b);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty[ob]);
+          ++oc;
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BNS>
+int launch_attn_bwd(const CUtensorMap& tmDO, const CUtensorMap& tmV, const CUtensorMap& tmK, const CUtensorMap& tmQ,
+                    const CUtensorMap& tmDV, const CUtensorMap& tmDQ, const CUtensorMap& tmDK, const AbParams& p,
+                    cudaStream_t stream) {
+  using Cfg = AbCfg<BNS>;
+  auto kern = attn_bwd_kernel<BNS>;
+  static std::atomic<int> attr_set[kMaxDevices];
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    D2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev].store(1, std::memory_order_release);
+  }
+  const int grid = p.units < num_sms() ? p.units : num_sms();
+  D2R_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), Cfg::SMEM_BYTES, stream, tmDO, tmV, tmK, tmQ, tmDV, tmDQ, tmDK, p));
+  count_launch();
+  return check_launch("attn_bwd_kernel");
+}
+
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 }  // namespace
@@ -456,6 +808,53 @@ int d2r_attn_fwd(const d2r_attn_args* a, void* stream) {
                        CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if (bns == 64) return launch_attn_fwd<64>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
   return launch_attn_fwd<128>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
+}
+
+int d2r_attn_bwd(const d2r_attn_bwd_args* a, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  D2R_CHECK_ARG(a != nullptr && a->d_out && a->p && a->q && a->k && a->v && a->dq && a->dk && a->dv,
+                "attn_bwd: null argument");
+  D2R_CHECK_ARG(a->B > 0 && a->heads > 0 && a->Lq > 0 && a->Lc > 0 && a->hd > 0, "attn_bwd: empty problem");
+  D2R_CHECK_ARG(a->Lc <= 128 && a->Lq <= 128,
+                "attn_bwd: at most 128 queries and keys per (sample, head) (got %d, %d): use the composed path",
+                a->Lq, a->Lc);
+  D2R_CHECK_ARG(a->hd % 16 == 0 && (a->hd <= 64 || a->hd % 64 == 0), "attn_bwd: head dim %d unsupported", a->hd);
+  D2R_CHECK_ARG(a->do_ld % 8 == 0 && a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->p_ld % 8 == 0 &&
+                    a->dq_ld % 8 == 0 && a->dk_ld % 8 == 0 && a->dv_ld % 8 == 0 && a->p_ld >= a->Lc,
+                "attn_bwd: leading dimensions must be multiples of 8 elements (TMA 16-byte rule)");
+  D2R_CHECK_ARG(aligned16(a->d_out) && aligned16(a->p) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) &&
+                    aligned16(a->dq) && aligned16(a->dk) && aligned16(a->dv),
+                "attn_bwd: operands must be 16-byte aligned");
+  const int bns = a->Lc <= 64 ? 64 : 128;
+  AbParams p;
+  p.Lq = a->Lq; p.Lc = a->Lc; p.hd = a->hd; p.heads = a->heads;
+  p.units = a->B * a->heads;
+  p.nkb = (a->hd + 63) / 64;
+  p.ksteps_q = (a->Lq + 15) / 16;
+  p.ksteps_c = (a->Lc + 15) / 16;
+  p.nt = a->hd <= 64 ? 64 : 128;
+  p.n_tiles = (a->hd + p.nt - 1) / p.nt;
+  p.alpha = a->alpha; p.sign = a->sign;
+  p.P = static_cast<const __nv_bfloat16*>(a->p);
+  p.p_ld = a->p_ld;
+  const long long H = a->heads, B = a->B;
+  CUtensorMap tmDO, tmV, tmK, tmQ, tmDV, tmDQ, tmDK;
+  int rc;
+  auto operand = [&](CUtensorMap* tm, const void* base, long long rows, long long ld, int box_rows) {
+    return encode_map(tm, base, 2, a->hd, rows, H, B, ld, a->hd, rows * ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  auto output = [&](CUtensorMap* tm, void* base, long long rows, long long ld) {
+    return encode_map(tm, base, 2, a->hd, rows, H, B, ld, a->hd, rows * ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  };
+  if ((rc = operand(&tmDO, a->d_out, a->Lq, a->do_ld, 128))) return rc;
+  if ((rc = operand(&tmV, a->v, a->Lc, a->v_ld, bns))) return rc;
+  if ((rc = operand(&tmK, a->k, a->Lc, a->k_ld, 128))) return rc;
+  if ((rc = operand(&tmQ, a->q, a->Lq, a->q_ld, 128))) return rc;
+  if ((rc = output(&tmDV, a->dv, a->Lc, a->dv_ld))) return rc;
+  if ((rc = output(&tmDQ, a->dq, a->Lq, a->dq_ld))) return rc;
+  if ((rc = output(&tmDK, a->dk, a->Lc, a->dk_ld))) return rc;
+  if (bns == 64) return launch_attn_bwd<64>(tmDO, tmV, tmK, tmQ, tmDV, tmDQ, tmDK, p, st);
+  return launch_attn_bwd<128>(tmDO, tmV, tmK, tmQ, tmDV, tmDQ, tmDK, p, st);
 }
 
 }  // extern "C"

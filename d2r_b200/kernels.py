@@ -130,6 +130,26 @@ def attn_fused_fwd(q: Tensor, q_ld: int, k: Tensor, k_ld: int, v: Tensor, v_ld: 
     return out, P, out2
 
 
+def attn_fused_bwd_supported(dtype: torch.dtype, Lq: int, Lc: int, hd: int) -> bool:
+    return attn_fused_supported(dtype, Lc, hd) and Lq <= 128
+
+
+def attn_fused_bwd(dO: Tensor, do_ld: int, sign: float, P: Tensor, q: Tensor, q_ld: int, k: Tensor, k_ld: int,
+                   v: Tensor, v_ld: int, dq: Tensor, dq_ld: int, dk: Tensor, dk_ld: int, dv: Tensor, dv_ld: int, *,
+                   B: int, Lq: int, Lc: int, D: int, heads: int, alpha: float) -> None:
+    """Backward of the attention core in one kernel; dq / dk / dv (possibly column slices, own row strides) are
+    overwritten.  P [B, heads, Lq, p_ld] from the forward."""
+    L.require_cuda(dO, P, q, k, v, dq, dk, dv)
+    a = L.AttnBwdArgs()
+    a.B, a.heads, a.Lq, a.Lc, a.hd = B, heads, Lq, Lc, D // heads
+    a.alpha, a.sign = alpha, sign
+    a.d_out, a.p, a.q, a.k, a.v = dO.data_ptr(), P.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.do_ld, a.p_ld, a.q_ld, a.k_ld, a.v_ld = do_ld, P.shape[-1], q_ld, k_ld, v_ld
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.dq_ld, a.dk_ld, a.dv_ld = dq_ld, dk_ld, dv_ld
+    L.check(L.lib.d2r_attn_bwd(C.byref(a), L.stream()), "attn_bwd")
+
+
 def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int = L.ACT_NONE,
            residual: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None,
            out: Optional[Tensor] = None, epilogue: int = L.EPI_STD, c2: Optional[Tensor] = None,

@@ -301,6 +301,10 @@ def attn_bwd(dO: Tensor, do_ld: int, sign: float, P: Tensor, q: Tensor, q_ld: in
     dh = D // heads
     Lcp = pad8(Lc)
     HS = heads * Lq * Lcp
+    if FUSED_ATTN and K.attn_fused_bwd_supported(cd, Lq, Lc, dh):
+        K.attn_fused_bwd(dO, do_ld, sign, P, q, q_ld, k, k_ld, v, v_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld,
+                         B=B, Lq=Lq, Lc=Lc, D=D, heads=heads, alpha=alpha)
+        return
     K.gemm(P, dO, dv, m=Lc, n=dh, k=Lq, lda=Lcp, ldb=do_ld, ldc=dv_ld, a_mn=True, b_mn=True, batch=B * heads,
            batch_inner=heads, a_str=(HS, Lq * Lcp), b_str=(Lq * do_ld, dh), c_str=(Lc * dv_ld, dh), alpha=sign)
     if _fused_softmax(cd, Lc):

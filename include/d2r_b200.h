@@ -124,6 +124,26 @@ typedef struct d2r_attn_args {
   int64_t r_ld;
 } d2r_attn_args;
 int d2r_attn_fwd(const d2r_attn_args* a, void* stream);
+/* Backward of the attention core in ONE kernel (Lq <= 128 and Lc <= 128): with P from the forward,
+ *   dP = sign * d_out V^T;  dS = alpha * P o (dP - rowsum(dP o P));  dq = dS K;  dk = dS^T Q;  dv = sign * P^T d_out.
+ * `sign` multiplies d_out (folds the minus of the squared-difference epilogue).  dq / dk / dv are overwritten, each
+ * addressed like its forward operand with its own row stride (they may be column slices of wider buffers). */
+typedef struct d2r_attn_bwd_args {
+  int32_t B, heads, Lq, Lc, hd;
+  int32_t reserved0;
+  float alpha, sign;
+  const void* d_out;     /* [B, Lq, heads*hd], row stride do_ld */
+  const void* p;         /* [B, heads, Lq, p_ld] */
+  const void* q;
+  const void* k;
+  const void* v;
+  int64_t do_ld, p_ld, q_ld, k_ld, v_ld;
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t dq_ld, dk_ld, dv_ld;
+} d2r_attn_bwd_args;
+int d2r_attn_bwd(const d2r_attn_bwd_args* a, void* stream);
 
 /* Row softmax over the last dim, optional scale: y = softmax(scale * x).  x fp32 or bf16
  * [rows, cols] with row stride ldx; y bf16 or fp32 with row stride ldy.

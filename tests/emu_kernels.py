@@ -68,6 +68,54 @@ def gemm(a, b, c, *, m, n, k, lda, ldb, ldc, a_mn=False, b_mn=False, batch=1, ba
     return c
 
 
+def attn_fused_supported(dtype, Lc, hd):
+    return dtype == torch.bfloat16 and Lc <= 128 and hd % 16 == 0 and (hd <= 64 or hd % 64 == 0)
+
+
+def attn_fused_bwd_supported(dtype, Lq, Lc, hd):
+    return attn_fused_supported(dtype, Lc, hd) and Lq <= 128
+
+
+def _heads(t, B, rows, heads, dh, ld):
+    """X[b, row, h*dh + c] with row stride ld -> view [B, heads, rows, dh]."""
+    assert ld % 8 == 0 and t.data_ptr() % 16 == 0, "TMA 16-byte rule"
+    return _view(t, (B, heads, rows, dh), (rows * ld, dh, ld, 1))
+
+
+def attn_fused_fwd(q, q_ld, k, k_ld, v, v_ld, *, B, Lq, Lc, D, heads, alpha, p_ld, residual=None, mode=0, out2=None):
+    dh = D // heads
+    assert attn_fused_supported(q.dtype, Lc, dh) and p_ld % 8 == 0 and p_ld >= Lc
+    Q, Kk, V = _heads(q, B, Lq, heads, dh, q_ld), _heads(k, B, Lc, heads, dh, k_ld), _heads(v, B, Lc, heads, dh, v_ld)
+    Pf = torch.softmax(alpha * (Q.float() @ Kk.float().transpose(-1, -2)), -1)
+    P = torch.zeros(B, heads, Lq, p_ld, dtype=torch.bfloat16)
+    P[..., :Lc] = Pf.to(torch.bfloat16)
+    o = (P[..., :Lc].float() @ V.float()).transpose(1, 2).reshape(B, Lq, D)
+    if mode == 1:
+        d = residual.float() - o
+        if out2 is None:
+            out2 = torch.empty(B, Lq, D, dtype=torch.bfloat16)
+        out2.copy_(d.to(torch.bfloat16))
+        o = d * d
+    elif residual is not None:
+        o = o + residual.float()
+    return o.to(torch.bfloat16), P, out2
+
+
+def attn_fused_bwd(dO, do_ld, sign, P, q, q_ld, k, k_ld, v, v_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld, *, B, Lq, Lc, D,
+                   heads, alpha):
+    dh = D // heads
+    assert attn_fused_bwd_supported(q.dtype, Lq, Lc, dh)
+    G = sign * _heads(dO, B, Lq, heads, dh, do_ld).float()
+    Q, Kk, V = (_heads(q, B, Lq, heads, dh, q_ld).float(), _heads(k, B, Lc, heads, dh, k_ld).float(),
+                _heads(v, B, Lc, heads, dh, v_ld).float())
+    Pf = P[..., :Lc].float()
+    dP = G @ V.transpose(-1, -2)
+    dS = (alpha * Pf * (dP - (dP * Pf).sum(-1, keepdim=True))).to(torch.bfloat16).float()
+    _heads(dv, B, Lc, heads, dh, dv_ld).copy_((Pf.transpose(-1, -2) @ G).to(dv.dtype))
+    _heads(dq, B, Lq, heads, dh, dq_ld).copy_((dS @ Kk).to(dq.dtype))
+    _heads(dk, B, Lc, heads, dh, dk_ld).copy_((dS.transpose(-1, -2) @ Q).to(dk.dtype))
+
+
 def softmax_fwd(x, cols, scale, out_dtype, ldy=None):
     ldy = ldy or x.shape[-1]
     y = torch.full(x.shape[:-1] + (ldy,), float("nan"), dtype=out_dtype)

@@ -51,9 +51,9 @@ def test_struct_sizes_match_c():
     prog = r'''
     #include <stdio.h>
     #include "d2r_b200.h"
-    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(d2r_gemm_args), sizeof(d2r_ptr8), sizeof(d2r_agg_args),
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(d2r_gemm_args), sizeof(d2r_ptr8), sizeof(d2r_agg_args),
                        sizeof(d2r_agg_bwd_args), sizeof(d2r_saf_args), sizeof(d2r_saf_bwd_args),
-                       sizeof(d2r_attn_args)); return 0; }
+                       sizeof(d2r_attn_args), sizeof(d2r_attn_bwd_args)); return 0; }
     '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -62,5 +62,5 @@ def test_struct_sizes_match_c():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     mine = [ctypes.sizeof(t) for t in (_lib.GemmArgs, _lib.Ptr8, _lib.AggArgs, _lib.AggBwdArgs, _lib.SafArgs,
-                                       _lib.SafBwdArgs, _lib.AttnArgs)]
+                                       _lib.SafBwdArgs, _lib.AttnArgs, _lib.AttnBwdArgs)]
     assert sizes == mine, (sizes, mine)

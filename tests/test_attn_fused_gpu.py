@@ -88,3 +88,73 @@ def test_attn_fused_rejects_unsupported_shapes():
     kv = torch.zeros(1, 200, 768, device="cuda", dtype=bf)
     with pytest.raises(RuntimeError):
         K.attn_fused_fwd(q, 768, kv, 768, kv, 768, B=1, Lq=8, Lc=200, D=768, heads=1, alpha=1.0, p_ld=200)
+
+
+@pytest.mark.parametrize("B,heads,Lq,Lc,D,alpha,sign", [
+    (3, 1, 128, 50, 768, 100.0 / math.sqrt(768), 1.0),
+    (3, 1, 50, 128, 768, 100.0 / math.sqrt(768), -1.0),     # the alignment cell folds a minus into d_out
+    (2, 1, 128, 128, 768, 1.0, 1.0),
+    (2, 1, 50, 50, 768, 1.0, 1.0),
+    (2, 16, 128, 128, 768, 1.0 / math.sqrt(48), 1.0),
+    (2, 16, 50, 50, 768, 1.0 / math.sqrt(48), 1.0),
+    (150, 1, 128, 50, 768, 3.6, 1.0),
+    (10, 16, 72, 56, 768, 0.15, 1.0),
+    (1, 1, 7, 3, 64, 1.0, 1.0),
+])
+def test_attn_fused_backward(B, heads, Lq, Lc, D, alpha, sign):
+    """dq / dk / dv of the fused backward against torch autograd through the same attention (fp32 math on the same
+    bf16 operands and the same bf16 P)."""
+    from d2r_b200 import kernels as K
+    torch.manual_seed(B * 31 + Lq + 3 * Lc)
+    scale = 0.25 if alpha > 1.5 else 1.0
+    q = (torch.randn(B, Lq, D, device="cuda") * scale).to(bf)
+    kv = (torch.randn(B, Lc, 2 * D, device="cuda") * scale).to(bf)
+    k, v = kv[:, :, :D], kv[:, :, D:]
+    dO = torch.randn(B, Lq, D, device="cuda").to(bf)
+    Lcp = (Lc + 7) // 8 * 8
+    out, P, _ = K.attn_fused_fwd(q, D, k, 2 * D, v, 2 * D, B=B, Lq=Lq, Lc=Lc, D=D, heads=heads, alpha=alpha, p_ld=Lcp)
+    dq = torch.full((B, Lq, D), float("nan"), device="cuda", dtype=bf)
+    dkv = torch.full((B, Lc, 2 * D), float("nan"), device="cuda", dtype=bf)
+    K.attn_fused_bwd(dO, D, sign, P, q, D, k, 2 * D, v, 2 * D, dq, D, dkv, 2 * D, dkv[:, :, D:], 2 * D,
+                     B=B, Lq=Lq, Lc=Lc, D=D, heads=heads, alpha=alpha)
+    torch.cuda.synchronize()
+    # reference: autograd through softmax attention in fp32 on the same bf16 values
+    dh = D // heads
+    qf = q.float().requires_grad_(True)
+    kf = k.float().contiguous().requires_grad_(True)
+    vf = v.float().contiguous().requires_grad_(True)
+    qh = qf.view(B, Lq, heads, dh).transpose(1, 2)
+    kh = kf.view(B, Lc, heads, dh).transpose(1, 2)
+    vh = vf.view(B, Lc, heads, dh).transpose(1, 2)
+    o = (torch.softmax(alpha * qh @ kh.transpose(-1, -2), -1) @ vh).transpose(1, 2).reshape(B, Lq, D)
+    o.backward(sign * dO.float())
+    def l2(a, b):
+        return ((a.float() - b).norm() / (b.norm() + 1e-12)).item()
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
+    # bf16 P / dS / outputs: a few 1e-3 .. 1e-2 relative in L2
+    assert l2(dkv[:, :, D:], vf.grad) <= 2e-2, ("dv", l2(dkv[:, :, D:], vf.grad))
+    assert l2(dq, qf.grad) <= 3e-2, ("dq", l2(dq, qf.grad))
+    assert l2(dkv[:, :, :D], kf.grad) <= 3e-2, ("dk", l2(dkv[:, :, :D], kf.grad))
+
+
+def test_attn_fused_backward_matches_composed_path():
+    import d2r_b200.stack as S
+    torch.manual_seed(1)
+    B, Lq, D, H = 4, 128, 768, 16
+    qkv = torch.randn(B, Lq, 3 * D, device="cuda").to(bf)
+    dy = torch.randn(B, Lq, D, device="cuda").to(bf)
+    alpha = 1.0 / math.sqrt(D // H)
+    res = []
+    try:
+        for fused in (True, False):
+            S.FUSED_ATTN = fused
+            _, P = S.attn_fwd(qkv, 3 * D, qkv[:, :, D:], 3 * D, qkv[:, :, 2 * D:], 3 * D, B, Lq, Lq, D, H, alpha, bf)
+            dqkv = torch.empty_like(qkv)
+            S.attn_bwd(dy, D, 1.0, P, qkv, 3 * D, qkv[:, :, D:], 3 * D, qkv[:, :, 2 * D:], 3 * D, dqkv, 3 * D,
+                       dqkv[:, :, D:], 3 * D, dqkv[:, :, 2 * D:], 3 * D, B, Lq, Lq, D, H, alpha, bf)
+            res.append(dqkv)
+    finally:
+        S.FUSED_ATTN = True
+    torch.cuda.synchronize()
+    a, b = res[0].float(), res[1].float()
+    assert ((a - b).norm() / b.norm()).item() <= 1e-2
