@@ -621,9 +621,10 @@ def kernel_roofline(fwd_bwd, K, torch):
         byts = (n_out + 2 * nfull) * x0.numel() * x0.element_size()
         return timed_call("agg", byts, orig["aggregate_bwd"], full, bvec, P, gate, final, d_outs, d_pooled, inputs)
 
-    def fused_wrap(fn):
+    def fused_wrap(fn, products):
+        # fused attention: `products` matrix products of 2 * B * Lq * Lc * D FLOP each (QK^T, PV | dP, dV, dQ, dK)
         def w(*a, **kw):
-            return timed_call("gemm", kw["flops"], fn, *a, **kw)
+            return timed_call("gemm", products * 2.0 * kw["B"] * kw["Lq"] * kw["Lc"] * kw["D"], fn, *a, **kw)
         return w
 
     import d2r_b200.lanes as LN
@@ -631,7 +632,7 @@ def kernel_roofline(fwd_bwd, K, torch):
     LN.ENABLED = False                  # one stream: concurrent lanes would overlap inside each other's event pairs
     K.gemm, K.aggregate_fwd, K.aggregate_bwd = gemm, agg_f, agg_b
     for n, fn in fused.items():
-        setattr(K, n, fused_wrap(fn))
+        setattr(K, n, fused_wrap(fn, 2 if n.endswith("fwd") else 4))
     serial_ms = 0.0
     try:
         fwd_bwd()                       # warm

@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libd2r_b200.so")
+# D2R_B200_LIB: bring-up / bisection only -- load another in-tree build of the same sources
+LIB_PATH = os.environ.get("D2R_B200_LIB") or os.path.join(_HERE, "csrc", "libd2r_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2

@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(kThreads) router_head_bwd_kernel(const float* 
   const int j = blockIdx.x;
   const long long b0 = (long long)blockIdx.y * kRhbTile;
   const int nb = (int)min((long long)kRhbTile, B - b0);
+  if (threadIdx.x < kRhbTile * kRhbMaxOut) s_dl[threadIdx.x / kRhbMaxOut][threadIdx.x % kRhbMaxOut] = 0.f;
+  __syncthreads();
   if ((int)threadIdx.x < kRhbTile * n_out) {
     const int t = threadIdx.x / n_out, i = threadIdx.x % n_out;
     float dl = 0.f;
