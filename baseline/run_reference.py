@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--text-len", type=int, default=128)
     ap.add_argument("--image-tokens", type=int, default=50)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--full", action="store_true",
+                    help="the whole UnimoModelF (encoders + stacks + head), loss = CE + js (unimo_model.py:149-162)")
     a = ap.parse_args()
     if a.device == "cpu":
         os.environ["CUDA_VISIBLE_DEVICES"] = ""
@@ -45,6 +47,8 @@ def main():
     if a.device == "cpu":
         torch.set_num_threads(a.threads or cores)
     dev = torch.device(a.device)
+    if a.full:
+        return run_full(a, dev, cores)
     torch.manual_seed(2023)
     args = RL.ref_args(DR_step=a.layers)
     mt = InteractionModule(args, num_layer_routing=a.layers, num_cells=6, path_hid=128).to(dev)
@@ -102,6 +106,44 @@ def main():
             "gpu": torch.cuda.get_device_name(0) if a.device == "cuda" else None,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30 if a.device == "cuda" else None}
     print(json.dumps(line), flush=True)
+
+
+def run_full(a, dev, cores):
+    import torch
+    from baseline.full_model import build_reference_model, synthetic_batch
+    model, _ = build_reference_model(a.layers, seed=2023)
+    model = model.to(dev).train(not a.eval)
+    batch = synthetic_batch(a.batch, a.text_len, seed=2023, device=dev)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        with torch.autocast(a.device, dtype=torch.bfloat16, enabled=a.bf16):
+            loss, logits = model(*batch)
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(a.warmup):
+        step()
+    ts = []
+    for _ in range(a.steps):
+        if a.device == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        if a.device == "cuda":
+            torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    print(json.dumps({"impl": "reference (unmodified UnimoModelF from baseline/_ref)", "device": a.device, "batch": a.batch,
+                      "steps": a.steps, "warmup": a.warmup, "mode": "train fwd+bwd", "dtype": "autocast-bf16" if a.bf16 else "fp32",
+                      "layers": a.layers, "text_len": a.text_len, "image_tokens": 50, "median_s_per_step": med,
+                      "mean_s_per_step": sum(ts) / len(ts), "samples_per_s": a.batch / med,
+                      "samples_per_s_mean": a.batch * len(ts) / sum(ts), "cores": cores,
+                      "threads": torch.get_num_threads() if a.device == "cpu" else None, "torch": torch.__version__,
+                      "gpu": torch.cuda.get_device_name(0) if a.device == "cuda" else None,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30 if a.device == "cuda" else None}), flush=True)
 
 
 if __name__ == "__main__":

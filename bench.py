@@ -50,6 +50,11 @@ CONFIGS = {
     "deep": dict(Lt=256, Li=197, R=4, B=256, train=True, idx=3,
                  desc="deep routing: both branches, bf16 fwd+bwd, K=6 cells, R=4 routing layers, text 256 + 197 image "
                       "tokens (ViT-B/16 patch count), hidden 768 (BASELINE configs[3])"),
+    "full": dict(Lt=128, Li=50, R=3, B=64, train=True, idx=2,
+                 desc="FULL D2R model (UnimoModelF: BERT-base + CLIP-ViT-B/32 towers on stock PyTorch feeding the routed "
+                      "stacks, random init), data-parallel training step fwd+bwd+gradient all-reduce, bf16 autocast, "
+                      "MVSA-shaped synthetic batches (max_seq 128, 224 px images -> 50 image tokens), R=3 "
+                      "(BASELINE configs[2])"),
     "eval-sweep": dict(Lt=128, Li=50, R=3, B=256, train=False, idx=4,
                        desc="inference-only (eval, no_grad) throughput sweep, both branches, bf16, K=6, R=3, text 128 "
                             "+ 50 image tokens, batch 2..4096 per GPU (BASELINE configs[4])"),
@@ -87,6 +92,14 @@ def useful_flops_per_sample(Lt, Li, layers):
     return layers * (layer(Lt, Li) + layer(Li, Lt))
 
 
+def metric_name(config):
+    if config == "full":
+        return "full-model samples/sec fwd+bwd (routed stack on d2r_b200, encoders stock PyTorch)"
+    if config == "eval-sweep":
+        return "routed-interaction samples/sec forward (eval, no_grad)"
+    return "routed-interaction samples/sec fwd+bwd"
+
+
 def workload_config(name, n_gpus, batch):
     c = CONFIGS[name]
     return {"workload": c["desc"], "batch_per_gpu": batch, "global_batch": batch * n_gpus, "text_len": c["Lt"],
@@ -105,6 +118,8 @@ def run_reference_subprocess(device, batch, steps, warmup, cfg, bf16=False, time
         cmd.append("--bf16")
     if not cfg["train"]:
         cmd.append("--eval")
+    if cfg.get("idx") == 2:
+        cmd.append("--full")
     env = dict(os.environ)
     if device == "cpu":
         env["CUDA_VISIBLE_DEVICES"] = ""
@@ -151,6 +166,8 @@ def cpu_baseline(cfg, steps, warmup):
     from baseline import ref_loader as RL
     cores = os.cpu_count() or 1
     what = "fwd+bwd" if cfg["train"] else "eval/no_grad forward"
+    if cfg.get("idx") == 2:
+        what = "fwd+bwd of the WHOLE model (encoders + stacks + head)"
     if RL.available():
         try:
             r = run_reference_subprocess("cpu", CPU_SAMPLE_BATCH, steps, warmup, cfg)
@@ -183,7 +200,7 @@ def reference_arm(args):
     # each step is a bounded sample (batch 8) of the workload: ~1-2 s of host time per step
     r = cpu_baseline(cfg, steps, warmup)
     line = {
-        "impl": "reference", "metric": "routed-interaction samples/sec fwd+bwd", "value": r["value"],
+        "impl": "reference", "metric": metric_name(args.config), "value": r["value"],
         "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -428,7 +445,7 @@ def own_arm(args):
         if stock and stock.get("value"):
             stock["speedup_of_this_repo"] = value / world / stock["value"]      # per GPU vs one B200
         line = {
-            "metric": "routed-interaction samples/sec fwd+bwd", "value": value, "unit": "samples/s",
+            "metric": metric_name(args.config), "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args.config, world, B),
@@ -457,6 +474,164 @@ def own_arm(args):
                              "traffic": AGG_TRAFFIC_BYTES, "traffic_note": AGG_TRAFFIC_NOTE},
             "cpu_baseline": cpu,
             "stock_pytorch_b200": stock,
+        }
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def full_arm(args):
+    """BASELINE configs[2]: the reference's whole model with the B200 stack swapped in (d2r_b200.integration.
+    accelerate), one process per GPU, batch sharded, one flat gradient all-reduce per step.  Rank 0 also times the
+    UNMODIFIED model on the same GPU (`stock_pytorch_b200`) before the swap.  Eager execution (the encoders are the
+    reference's stock PyTorch code); `value` has the batch resident in HBM, `e2e` copies it from pinned host memory."""
+    import torch
+    import torch.distributed as dist
+    from baseline.full_model import build_reference_model, synthetic_batch
+    from d2r_b200 import kernels as K
+    from d2r_b200.dp import FlatGradReducer
+    from d2r_b200.integration import accelerate
+    cfg = CONFIGS["full"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch_per_gpu or cfg["B"]
+    model, _ = build_reference_model(cfg["R"], seed=2023)
+    model = model.to(dev).train()
+    host = [t.pin_memory() for t in synthetic_batch(B, cfg["Lt"], seed=2023 + rank)]
+    devb = [t.to(dev) for t in host]
+
+    def fwd_bwd(batch):
+        for p in model.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, logits = model(*batch)
+        loss.backward()
+        return loss
+
+    def time_steps(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    stock = None
+    if rank == 0:
+        try:
+            ms_stock = 0.0
+            for _ in range(2):
+                fwd_bwd(devb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                float(fwd_bwd(devb).detach())
+            e1.record()
+            torch.cuda.synchronize()
+            ms_stock = e0.elapsed_time(e1) / 5
+            stock = {"value": B / (ms_stock / 1e3), "unit": "samples/s", "ms_per_step": ms_stock, "batch": B,
+                     "dtype": "torch.autocast(bfloat16)",
+                     "note": "the UNMODIFIED UnimoModelF (baseline/_ref) on this GPU, eager PyTorch, fwd+bwd+loss read, "
+                             "5 steps after 2 warm-up, no all-reduce"}
+        except Exception as e:
+            stock = {"value": None, "unavailable": f"{type(e).__name__}: {e}"}
+    accelerate(model)
+    reducer = FlatGradReducer(model.parameters())
+    h_loss = torch.empty(1).pin_memory()
+
+    def step(from_host=False):
+        if from_host:
+            for d, h in zip(devb, host):
+                d.copy_(h, non_blocking=True)
+        loss = fwd_bwd(devb)
+        reducer.step()
+        if from_host:
+            h_loss.copy_(loss.detach().float().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return loss
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = K.L.launch_count()
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = K.L.launch_count() - n0
+    ms = time_steps(step, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = time_steps(lambda: step(True), args.steps, 2)
+    # share of the routed stacks in the step: the two stacks alone, same batch, same precision
+    ms_stack = None
+    if rank == 0:
+        bb = model.model
+        t_in = torch.randn(B, cfg["Lt"], D, device=dev, requires_grad=True)
+        i_in = torch.randn(B, cfg["Li"], D, device=dev, requires_grad=True)
+
+        def stack_only():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                o1, s1 = bb.itr_module(t_in, i_in)
+                o2, s2 = bb.Reversed_itr_module(t_in, i_in)
+            (o1[0].sum() + s1.sum() + o2[0].sum() + s2.sum()).backward()
+        for _ in range(3):
+            stack_only()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            stack_only()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_stack = e0.elapsed_time(e1) / 5
+    if rank == 0:
+        samples = B * world * args.steps
+        value = samples / (ms / 1e3)
+        if stock and stock.get("value"):
+            stock["speedup_of_this_repo"] = value / world / stock["value"]
+        nparams = sum(p.numel() for p in model.parameters())
+        line = {
+            "metric": metric_name("full"), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config("full", world, B),
+            "engine": {"cuda_graph": False, "swap": "d2r_b200.integration.accelerate (stacks via run_pair, CLS poolers, "
+                                                    "Block fusion, js_div)",
+                       "allreduce": f"one flat fp32 bucket per step, {reducer.dead} never-used tensors excluded",
+                       "parameters_M": nparams / 1e6},
+            "clocks": clocks,
+            "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+            "stack_only_ms_per_step": ms_stack,
+            "stack_share_of_step": (ms_stack / (ms / args.steps)) if ms_stack else None,
+            "roofline": {"bound": "tensor", "kernel": "whole step, reference-executed FLOPs of the model (SURVEY §7: 52.5 "
+                                                      "GFLOP/sample forward, x3 for fwd+bwd)",
+                         "achieved": value / world * 3 * 52.5e9 / 1e12,
+                         "peak": load_peaks().get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
+                         "frac": value / world * 3 * 52.5e9 / 1e12 / load_peaks().get("bf16_tflops_sustained", 1400.0),
+                         "traffic": None},
+            "stock_pytorch_b200": stock,
+            "cpu_baseline": cpu_baseline(cfg, steps=3, warmup=1),
         }
         emit(line)
     if world > 1:
@@ -569,7 +744,7 @@ def eval_sweep(args, cfg, mt, mi, dev, rank, world, local):
         for p in ok:
             p["frac_of_tensor_peak"] = p["samples_per_s"] / world * fl / 1e12 / tc_peak
         cpu = cpu_baseline(cfg, steps=5, warmup=1)
-        line = {"metric": "routed-interaction samples/sec forward (eval, no_grad)", "value": best["samples_per_s"],
+        line = {"metric": metric_name("eval-sweep"), "value": best["samples_per_s"],
                 "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -691,7 +866,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--config", default="stack", choices=sorted(CONFIGS),
-                    help="stack = BASELINE configs[1] (the headline); deep = configs[3]; eval-sweep = configs[4]")
+                    help="stack = BASELINE configs[1] (the headline); full = configs[2] (whole model, encoders on stock "
+                         "PyTorch); deep = configs[3]; eval-sweep = configs[4]")
     ap.add_argument("--serial-branches", action="store_true",
                     help="call the two branch modules back to back instead of run_pair (two CUDA streams)")
     ap.add_argument("--overlap-allreduce", action="store_true",
@@ -710,6 +886,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config == "full":
+        return full_arm(args)
     return own_arm(args)
 
 

@@ -179,6 +179,62 @@ class GradAllReducer:
         self._settle()                        # p.grad -> views of the reduced bucket, as after step()
 
 
+class FlatGradReducer:
+    """Mean all-reduce of the gradients of an arbitrary parameter list through ONE flat fp32 bucket -- the whole
+    reference model (encoders on stock PyTorch + the routed stacks) under data parallelism.  The live set is fixed
+    at the first ``step()``: parameters whose ``.grad`` is still None after a backward never receive one in this
+    model (110 of the 1184 tensors of UnimoModelF, SURVEY §8e caveat 3) and are left out of the bucket, so no
+    unused-parameter search runs per step."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+        self.all_params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.params: Optional[List[torch.nn.Parameter]] = None
+        self.flat: Optional[torch.Tensor] = None
+        self._views: List[torch.Tensor] = []
+
+    def _plan(self) -> None:
+        self.params = [p for p in self.all_params if p.grad is not None]
+        if not self.params:
+            raise RuntimeError("FlatGradReducer: no parameter has a gradient (call after backward)")
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, device=self.params[0].device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    @property
+    def dead(self) -> int:
+        return len(self.all_params) - len(self.params or [])
+
+    def pack(self) -> torch.Tensor:
+        if self.params is None:
+            self._plan()
+        missing = sum(1 for p in self.params if p.grad is None)
+        if missing:
+            raise RuntimeError(f"FlatGradReducer: {missing} planned parameters have no gradient this step")
+        torch._foreach_copy_(self._views, [p.grad for p in self.params])
+        return self.flat
+
+    def all_reduce(self) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            if self.flat.is_cuda:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.div_(dist.get_world_size(self.group))
+
+    def finish(self) -> None:
+        for p, v in zip(self.params, self._views):
+            p.grad = v
+
+    def step(self) -> None:
+        self.pack()
+        self.all_reduce()
+        self.finish()
+
+
 class InputPrefetcher:
     """Host -> device input pipeline of one rank: the pinned host batch of step i+1 is copied to the GPU on a copy
     stream while step i computes, then moved into the (static, CUDA-graph visible) input tensors with a
