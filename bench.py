@@ -427,12 +427,13 @@ def own_arm(args):
 
     # --- per-kernel roofline pass (separate, eager, CUDA events around every tensor-core / aggregation launch) -----
     # (branches back to back here: kernels of concurrent streams would overlap inside each other's event pairs)
-    roof, hbm = kernel_roofline(lambda: fwd_bwd(serial=True, reduce=False), K, torch) if rank == 0 else (None, None)
+    peaks = load_peaks()
+    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roof, hbm = (kernel_roofline(lambda: fwd_bwd(serial=True, reduce=False), K, torch, tc_peak, hbm_peak)
+                 if rank == 0 else (None, None))
 
     if rank == 0:
-        peaks = load_peaks()
-        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback"
         samples = B * world * args.steps
         value = samples / (ms / 1e3)
@@ -459,12 +460,25 @@ def own_arm(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": {
-                "bound": "tensor", "kernel": "tcgen05 kernels of one fwd+bwd step (gemm_tc*_kernel + fused attention)",
-                "achieved": roof["tflops"], "peak": tc_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tc_peak,
+                "bound": "tensor",
+                "kernel": "gemm_tc2_kernel / gemm_tc_kernel: the tensor-bound tcgen05 launches of one fwd+bwd step "
+                          "(arithmetic intensity above the ridge point: the projections, their data- and weight-gradients)",
+                "achieved": roof["classes"]["tensor"]["achieved_tflops"], "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": roof["classes"]["tensor"]["frac_of_tensor_peak"],
                 "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE, "peak_source": peak_src,
-                "launches_per_step": roof["launches"], "kernel_ms_per_step": roof["ms"],
+                "launches_per_step": roof["classes"]["tensor"]["launches"],
+                "kernel_ms_per_step": roof["classes"]["tensor"]["ms"],
                 "single_stream_step_ms": roof["serial_step_ms"],
-                "kernel_share_of_step": roof["ms"] / roof["serial_step_ms"],
+                "kernel_share_of_step": roof["classes"]["tensor"]["ms"] / roof["serial_step_ms"],
+                "ridge_flop_per_byte": roof["ridge_flop_per_byte"],
+                "classes": roof["classes"],
+                "all_tcgen05_launches": {"launches_per_step": roof["launches"], "kernel_ms_per_step": roof["ms"],
+                                         "achieved": roof["tflops"], "frac": roof["tflops"] / tc_peak,
+                                         "note": "round-1 definition: FLOPs of every tcgen05 launch (HBM- and "
+                                                 "latency-bound ones included) over their summed time"},
+                "vendor_calibration": "cuBLAS on this GPU, same shapes, isolated: 944 TF/s (m=32768 n=768 k=768; this "
+                                      "kernel 899), 737 (m=12800; 567), 1490 (k=4608; 1326), 1333 (n=4608; 1326): "
+                                      "profiles/r02_vendor_calibration.txt",
                 "step_algorithmic_tflops": flops_step / (ms / args.steps / 1e3) / 1e12,
                 "step_frac_of_peak": flops_step / (ms / args.steps / 1e3) / 1e12 / tc_peak,
             },
@@ -763,8 +777,16 @@ def eval_sweep(args, cfg, mt, mi, dev, rank, world, local):
     return 0
 
 
-def kernel_roofline(fwd_bwd, K, torch):
-    """Run two eager steps with CUDA events around each tensor-core launch and each aggregation launch."""
+def kernel_roofline(fwd_bwd, K, torch, tc_peak, hbm_peak):
+    """Two eager single-stream steps with CUDA events around every tensor-core launch (d2r_gemm on bf16 operands,
+    fused attention) and every aggregation launch.  Each tensor-core launch is put in a roofline class by its
+    ARITHMETIC INTENSITY (algorithmic FLOPs / algorithmic bytes, every distinct operand read or written once):
+      tensor   intensity >= ridge point (measured bf16 peak / measured HBM bandwidth, ~209 FLOP/B): the projections
+      hbm      intensity below the ridge: the attention products (34 .. 130 FLOP/B) -- bandwidth-bound by the model
+      latency  launches whose roofline time is under 4 us (the [B,768] global-branch GEMMs): bound by launch and
+               pipeline-fill latency, reported with their count and time only
+    """
+    ridge = tc_peak * 1e12 / (hbm_peak * 1e9)
     recs = {"gemm": [], "agg": []}
     orig = {n: getattr(K, n) for n in ("gemm", "aggregate_fwd", "aggregate_bwd")}
     fused = {n: getattr(K, n) for n in ("attn_fused_fwd", "attn_fused_bwd") if hasattr(K, n)}
@@ -780,7 +802,11 @@ def kernel_roofline(fwd_bwd, K, torch):
     def gemm(a, b, c, **kw):
         if a.dtype != torch.bfloat16:
             return orig["gemm"](a, b, c, **kw)
-        return timed_call("gemm", 2.0 * kw["m"] * kw["n"] * kw["k"] * kw.get("batch", 1), orig["gemm"], a, b, c, **kw)
+        m, n, k, z = kw["m"], kw["n"], kw["k"], kw.get("batch", 1)
+        byts = z * ((m * k + n * k) * 2 + m * n * c.element_size())
+        if kw.get("residual") is not None:
+            byts += z * m * n * kw["residual"].element_size()
+        return timed_call("gemm", (2.0 * m * n * k * z, float(byts)), orig["gemm"], a, b, c, **kw)
 
     def agg_f(full, bvec, P, gate, final, inputs=None, want_pooled=True):
         x0 = full[0]
@@ -796,10 +822,15 @@ def kernel_roofline(fwd_bwd, K, torch):
         byts = (n_out + 2 * nfull) * x0.numel() * x0.element_size()
         return timed_call("agg", byts, orig["aggregate_bwd"], full, bvec, P, gate, final, d_outs, d_pooled, inputs)
 
-    def fused_wrap(fn, products):
-        # fused attention: `products` matrix products of 2 * B * Lq * Lc * D FLOP each (QK^T, PV | dP, dV, dQ, dK)
+    def fused_wrap(fn, fwd):
+        # fused attention: 2 (forward: QK^T, PV) or 4 (backward: dP, dV, dQ, dK) products of 2 B Lq Lc D FLOP each
         def w(*a, **kw):
-            return timed_call("gemm", products * 2.0 * kw["B"] * kw["Lq"] * kw["Lc"] * kw["D"], fn, *a, **kw)
+            B_, Lq, Lc, D_, H = kw["B"], kw["Lq"], kw["Lc"], kw["D"], kw["heads"]
+            if fwd:
+                el = Lq * D_ * (3 if kw.get("residual") is not None else 2) + 2 * Lc * D_ + H * Lq * Lc
+            else:
+                el = 3 * Lq * D_ + 4 * Lc * D_ + H * Lq * Lc
+            return timed_call("gemm", ((2 if fwd else 4) * 2.0 * B_ * Lq * Lc * D_, 2.0 * B_ * el), fn, *a, **kw)
         return w
 
     import d2r_b200.lanes as LN
@@ -807,7 +838,7 @@ def kernel_roofline(fwd_bwd, K, torch):
     LN.ENABLED = False                  # one stream: concurrent lanes would overlap inside each other's event pairs
     K.gemm, K.aggregate_fwd, K.aggregate_bwd = gemm, agg_f, agg_b
     for n, fn in fused.items():
-        setattr(K, n, fused_wrap(fn, 2 if n.endswith("fwd") else 4))
+        setattr(K, n, fused_wrap(fn, n.endswith("fwd")))
     serial_ms = 0.0
     try:
         fwd_bwd()                       # warm
@@ -830,12 +861,35 @@ def kernel_roofline(fwd_bwd, K, torch):
         for n, fn in fused.items():
             setattr(K, n, fn)
         LN.ENABLED = lanes_were
-    gms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["gemm"]) / nsteps
-    gfl = sum(w for _, _, w in recs["gemm"]) / nsteps
+    cls = {c: {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0} for c in ("tensor", "hbm", "latency")}
+    for e0, e1, (fl, by) in recs["gemm"]:
+        t_roof_us = max(fl / (tc_peak * 1e12), by / (hbm_peak * 1e9)) * 1e6
+        c = "latency" if t_roof_us < 4.0 else ("tensor" if fl / by >= ridge else "hbm")
+        d = cls[c]
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    for d in cls.values():
+        for k in d:
+            d[k] /= nsteps
+    gms = sum(d["ms"] for d in cls.values())
+    gfl = sum(d["flops"] for d in cls.values())
     ams = sum(e0.elapsed_time(e1) for e0, e1, _ in recs["agg"]) / nsteps
     aby = sum(w for _, _, w in recs["agg"]) / nsteps
-    return ({"tflops": gfl / (gms / 1e3) / 1e12, "ms": gms, "launches": len(recs["gemm"]) // nsteps,
-             "serial_step_ms": serial_ms},
+    t = cls["tensor"]
+    h = cls["hbm"]
+    return ({"tflops": gfl / (gms / 1e3) / 1e12, "ms": gms, "launches": int(sum(d["launches"] for d in cls.values())),
+             "serial_step_ms": serial_ms, "ridge_flop_per_byte": ridge,
+             "classes": {
+                 "tensor": {"launches": int(t["launches"]), "ms": t["ms"],
+                            "achieved_tflops": t["flops"] / (t["ms"] / 1e3) / 1e12 if t["ms"] else None,
+                            "frac_of_tensor_peak": t["flops"] / (t["ms"] / 1e3) / 1e12 / tc_peak if t["ms"] else None},
+                 "hbm": {"launches": int(h["launches"]), "ms": h["ms"],
+                         "achieved_gbs": h["bytes"] / (h["ms"] / 1e3) / 1e9 if h["ms"] else None,
+                         "frac_of_hbm_peak": h["bytes"] / (h["ms"] / 1e3) / 1e9 / hbm_peak if h["ms"] else None,
+                         "achieved_tflops": h["flops"] / (h["ms"] / 1e3) / 1e12 if h["ms"] else None},
+                 "latency": {"launches": int(cls["latency"]["launches"]), "ms": cls["latency"]["ms"]}}},
             {"gbs": aby / (ams / 1e3) / 1e9, "ms": ams, "launches": len(recs["agg"]) // nsteps})
 
 
