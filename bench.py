@@ -570,8 +570,17 @@ def full_arm(args):
                              "5 steps after 2 warm-up, no all-reduce"}
         except Exception as e:
             stock = {"value": None, "unavailable": f"{type(e).__name__}: {e}"}
-    accelerate(model)
+    accelerate(model, graph=not args.no_graph)
     reducer = FlatGradReducer(model.parameters())
+    graphed = not args.no_graph
+    try:
+        fwd_bwd(devb)                 # first call builds the CUDA graphs of the two stacks
+        torch.cuda.synchronize()
+    except Exception as e:
+        sys.stderr.write(f"[bench] graphing the stacks failed ({type(e).__name__}: {e}); eager stacks\n")
+        torch.cuda.synchronize()
+        model.model.itr_module.__dict__["_d2r_graph"] = False
+        graphed = False
     h_loss = torch.empty(1).pin_memory()
 
     def step(from_host=False):
@@ -627,8 +636,8 @@ def full_arm(args):
             "metric": metric_name("full"), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config("full", world, B),
-            "engine": {"cuda_graph": False, "swap": "d2r_b200.integration.accelerate (stacks via run_pair, CLS poolers, "
-                                                    "Block fusion, js_div)",
+            "engine": {"cuda_graph": "the two stacks (forward graph + backward graph); encoders eager" if graphed else False,
+                       "swap": "d2r_b200.integration.accelerate (stacks via run_pair, CLS poolers, Block fusion, js_div)",
                        "allreduce": f"one flat fp32 bucket per step, {reducer.dead} never-used tensors excluded",
                        "parameters_M": nparams / 1e6},
             "clocks": clocks,

@@ -330,9 +330,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int cpo = nco >> 1;
       for (int t = 0; t < p.n_tiles; ++t) {
         const int ob = oc & 1;
+        // The residual of this tile's chunks is fetched BEFORE waiting for the accumulator: eight independent 16-byte
+        // loads per thread in flight under the MMA wait.  (First version: one load at a time behind the wait, each
+        // followed by its unpack -- ncu showed 44 % of the kernel's stall samples on those four LDG.128.)
+        uint4 rr[2][4];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col0 = t * p.nt + (half * cpo + cc) * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            // hd is a multiple of 8: a group of 8 columns is entirely inside or outside the head
+            const bool ok = rrow != nullptr && cc < cpo && row_ok && col0 + g * 8 < p.hd;
+            rr[cc][g] = ok ? __ldg(reinterpret_cast<const uint4*>(rrow + col0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
         tc_fence_after();
-        for (int cc = 0; cc < cpo; ++cc) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (cc >= cpo) break;
           const int c = half * cpo + cc;
           const int col0 = t * p.nt + c * 32;   // column inside the head
           if (col0 >= p.hd) continue;
@@ -343,11 +359,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (rrow != nullptr) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float t8[8];
-              const int nvalid = row_ok ? max(0, min(8, p.hd - col0 - g * 8)) : 0;
-              ld_group(rrow + col0 + g * 8, t8, nvalid);
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rr[cc][g]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) res[g * 8 + j] = t8[j];
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(hh[j]);
+                res[g * 8 + 2 * j] = f.x;
+                res[g * 8 + 2 * j + 1] = f.y;
+              }
             }
           }
           tmem_ld_wait();
@@ -647,9 +665,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_constant_
         tmem_ld32(ts + c * 32, ra);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float pr[8];
-          ld_group(prow + c * 32 + g * 8, pr, row_ok ? max(0, min(8, p.Lc - c * 32 - g * 8)) : 0);
-          pk[cc][g] = pack8_bf16(pr);            // exact: P is bf16 in memory
+          // 16-byte loads issued back to back (the row is padded to p_ld, a multiple of 8): the ragged tail of the
+          // last group is masked below, columns the forward never wrote are never used
+          const int col0 = c * 32 + g * 8;
+          pk[cc][g] = (row_ok && col0 < p.Lc) ? __ldg(reinterpret_cast<const uint4*>(prow + col0))
+                                              : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col0 = c * 32 + g * 8;
+          if (col0 < p.Lc && col0 + 8 > p.Lc) {
+            __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(&pk[cc][g]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + j >= p.Lc) h16[j] = __float2bfloat16_rn(0.f);
+          }
         }
         tmem_ld_wait();
 #pragma unroll

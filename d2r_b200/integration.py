@@ -31,6 +31,37 @@ from .interaction.InteractionModule import InteractionModule, Reversed_Interacti
 from .interaction.XModules import Block, js_div
 
 
+class _PairModule(nn.Module):
+    """Both stacks as one callable with tensor-only inputs / outputs (what torch.cuda.make_graphed_callables wants).
+    A helper object: it is never attached to the model, so it does not show up in the model's state_dict."""
+
+    def __init__(self, itr, rev):
+        super().__init__()
+        self.itr, self.rev = itr, rev
+
+    def forward(self, text, image):
+        (ot, st), (oi, si) = run_pair(self.itr, self.rev, text, image)
+        return ot[0], st, oi[0], si
+
+
+def _graphed_pair(itr, rev, text, image):
+    """CUDA-graph the two stacks (forward graph + backward graph, torch.cuda.make_graphed_callables) for this input
+    signature.  Inside an otherwise eager model the ~1400 launches of the stacks cost more host time than GPU time at
+    small batches; replaying them as two graph launches removes that.  BatchNorm running statistics are restored
+    after the warm-up / capture passes (they run the forward four times on the sample)."""
+    import contextlib
+    bufs = [(b, b.detach().clone()) for m in (itr, rev) for b in m.buffers()]
+    bf16 = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False) if bf16 else contextlib.nullcontext()
+    sample = (text.detach().clone().requires_grad_(True), image.detach().clone().requires_grad_(True))
+    with ctx:
+        fn = torch.cuda.make_graphed_callables(_PairModule(itr, rev), sample, allow_unused_input=True)
+    with torch.no_grad():
+        for b, saved in bufs:
+            b.copy_(saved)
+    return fn
+
+
 class _PairedInteraction(InteractionModule):
     """First of the two back-to-back stack calls: runs both stacks concurrently, parks the partner's result."""
 
@@ -38,6 +69,17 @@ class _PairedInteraction(InteractionModule):
         partner = self.__dict__.get("_d2r_partner")
         if partner is None or return_path_probs:
             return super().forward(text, image, return_path_probs)
+        if (self.__dict__.get("_d2r_graph") and torch.is_grad_enabled() and text.requires_grad and image.requires_grad
+                and not torch.cuda.is_current_stream_capturing()):
+            cache = self.__dict__.setdefault("_d2r_graph_cache", {})
+            key = (tuple(text.shape), tuple(image.shape), text.dtype, image.dtype, self.training,
+                   torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda"))
+            fn = cache.get(key)
+            if fn is None:
+                fn = cache[key] = _graphed_pair(self, partner, text, image)
+            ot, st, oi, si = fn(text, image)
+            partner.__dict__["_d2r_parked"] = (text, image, ([oi], si))
+            return [ot], st
         mine, other = run_pair(self, partner, text, image)
         partner.__dict__["_d2r_parked"] = (text, image, other)
         return mine
@@ -78,9 +120,10 @@ def _find_backbone(model: nn.Module) -> nn.Module:
     raise RuntimeError("d2r_b200.accelerate: no module with itr_module / Reversed_itr_module found")
 
 
-def accelerate(model: nn.Module, *, pair: bool = True, head: bool = True) -> nn.Module:
+def accelerate(model: nn.Module, *, pair: bool = True, head: bool = True, graph: bool = False) -> nn.Module:
     """See module docstring.  ``pair=False`` keeps the two stack calls separate; ``head=False`` leaves the CLS
-    poolers, the Block fusion and js_div on the reference's PyTorch code."""
+    poolers, the Block fusion and js_div on the reference's PyTorch code; ``graph=True`` (needs ``pair``) replays the
+    two stacks from CUDA graphs in training (static shapes per graph; one graph pair per input signature)."""
     bb = _find_backbone(model)
     ref_t, ref_i = bb.itr_module, bb.Reversed_itr_module
     args = ref_t.args
@@ -94,6 +137,7 @@ def accelerate(model: nn.Module, *, pair: bool = True, head: bool = True) -> nn.
     bb.Reversed_itr_module = _rebind(new_i, ref_i)
     if pair:
         new_t.__dict__["_d2r_partner"] = new_i
+        new_t.__dict__["_d2r_graph"] = bool(graph)
     if head:
         for name in ("text_pool", "vision_pool"):
             old = getattr(bb, name)
@@ -108,5 +152,5 @@ def accelerate(model: nn.Module, *, pair: bool = True, head: bool = True) -> nn.
         mod = sys.modules.get(type(bb).__module__)
         if mod is not None and hasattr(mod, "js_div"):
             mod.js_div = js_div          # the symbol modeling_unimo.py:849 resolves at call time
-    model.__dict__["_d2r_accelerated"] = dict(pair=pair, head=head)
+    model.__dict__["_d2r_accelerated"] = dict(pair=pair, head=head, graph=bool(graph and pair))
     return model

@@ -43,25 +43,71 @@ def test_accelerated_full_model_logits_match_reference_fp32():
 
 
 def test_accelerated_full_model_trains():
-    """Train mode, bf16 autocast: finite loss close to the reference's, every parameter the reference trains gets a
-    gradient and the never-used ones (SURVEY §8e caveat 3) stay without one."""
+    """Train-mode arithmetic (BatchNorm batch statistics) under bf16 autocast: finite loss close to the reference's,
+    every parameter the reference trains gets a gradient and the never-used ones (SURVEY §8e caveat 3) stay without
+    one.  The whole-model gradient is judged against the reference's fp32 run with the reference's own autocast run
+    as the yardstick: two different bf16 evaluations of the routed stacks disagree by several per cent in what they
+    send back into the 300 M encoder parameters (measured cosine 0.95 between them), which says nothing about either."""
     ref, acc, synthetic_batch = _models()
     batch = synthetic_batch(4, 32, seed=4, device="cuda")
     for m in (ref, acc):
-        m.eval()          # no dropout: the two runs must see the same network
+        m.eval()          # no dropout: the runs must see the same network
         for mod in m.modules():
             if isinstance(mod, torch.nn.BatchNorm1d):
                 mod.train()
-    out = {}
-    for name, m in (("ref", ref), ("acc", acc)):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+
+    def run(m, bf16):
+        for p in m.parameters():
+            p.grad = None
+        bufs = [(b, b.detach().clone()) for b in m.buffers()]
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
             loss, logits = m(*batch)
         loss.backward()
-        out[name] = (loss.item(), logits.float(), {n for n, p in m.named_parameters() if p.grad is None})
-    assert torch.isfinite(out["acc"][1]).all()
-    assert abs(out["acc"][0] - out["ref"][0]) <= 5e-2 * max(1.0, abs(out["ref"][0]))
-    assert out["acc"][2] == out["ref"][2] and len(out["ref"][2]) == 110
-    g_r = torch.cat([p.grad.flatten().float() for n, p in ref.named_parameters() if p.grad is not None])
-    g_a = torch.cat([p.grad.flatten().float() for n, p in acc.named_parameters() if p.grad is not None])
-    cos = torch.dot(g_r, g_a) / (g_r.norm() * g_a.norm())
-    assert cos.item() >= 0.98, cos.item()
+        with torch.no_grad():
+            for b, saved in bufs:
+                b.copy_(saved)
+        none = {n for n, p in m.named_parameters() if p.grad is None}
+        g = torch.cat([p.grad.flatten().float() for n, p in m.named_parameters() if p.grad is not None])
+        return loss.item(), logits.float(), none, g
+
+    l32, _, none32, g32 = run(ref, False)
+    lr, logits_r, none_r, gr = run(ref, True)
+    la, logits_a, none_a, ga = run(acc, True)
+    assert torch.isfinite(logits_a).all() and torch.isfinite(ga).all()
+    assert abs(la - l32) <= max(5e-2, 2 * abs(lr - l32)) * max(1.0, abs(l32)), (la, lr, l32)
+    assert none_a == none_r == none32 and len(none32) == 110
+    cos = lambda a, b: (torch.dot(a, b) / (a.norm() * b.norm())).item()
+    c_acc, c_ref = cos(ga, g32), cos(gr, g32)
+    assert c_acc >= c_ref - 0.02, (c_acc, c_ref)
+
+
+def test_accelerated_full_model_graphed_stacks_match_eager():
+    """accelerate(graph=True): the two stacks replayed from CUDA graphs inside the eager model give the eager result."""
+    ref, acc, synthetic_batch = _models()
+    del ref
+    batch = synthetic_batch(4, 32, seed=6, device="cuda")
+    acc.eval()
+    for mod in acc.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.train()
+
+    def run():
+        for p in acc.parameters():
+            p.grad = None
+        bufs = [(b, b.detach().clone()) for b in acc.buffers()]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, logits = acc(*batch)
+        loss.backward()
+        with torch.no_grad():
+            for b, saved in bufs:
+                b.copy_(saved)
+        g = torch.cat([p.grad.flatten().float() for p in acc.parameters() if p.grad is not None])
+        return loss.item(), logits.float().clone(), g
+
+    l0, lg0, g0 = run()
+    acc.model.itr_module.__dict__["_d2r_graph"] = True
+    for _ in range(2):                        # first call captures, second replays
+        l1, lg1, g1 = run()
+    assert abs(l1 - l0) <= 1e-3 * max(1.0, abs(l0))
+    assert ((lg1 - lg0).abs().max() / lg0.abs().max()).item() <= 1e-3
+    assert ((g1 - g0).norm() / g0.norm()).item() <= 2e-2       # atomically accumulated gradients differ in rounding
