@@ -490,6 +490,11 @@ def own_arm(args):
             "stock_pytorch_b200": stock,
         }
         emit(line)
+    # every rank drops its CUDA graph (it holds captured NCCL kernels in the overlapped mode) before the
+    # communicator goes away: destroying the process group under a live graph was round 1's "unexplained error
+    # after the result line"
+    graph = static_loss = None
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
