@@ -123,7 +123,8 @@ def _find_backbone(model: nn.Module) -> nn.Module:
 def accelerate(model: nn.Module, *, pair: bool = True, head: bool = True, graph: bool = False) -> nn.Module:
     """See module docstring.  ``pair=False`` keeps the two stack calls separate; ``head=False`` leaves the CLS
     poolers, the Block fusion and js_div on the reference's PyTorch code; ``graph=True`` (needs ``pair``) replays the
-    two stacks from CUDA graphs in training (static shapes per graph; one graph pair per input signature)."""
+    two stacks from CUDA graphs in training (static shapes per graph; one graph pair per input signature; switch it on
+    before the model's first forward -- the graphs are captured at the first training call of each signature)."""
     bb = _find_backbone(model)
     ref_t, ref_i = bb.itr_module, bb.Reversed_itr_module
     args = ref_t.args

@@ -82,32 +82,36 @@ def test_accelerated_full_model_trains():
 
 
 def test_accelerated_full_model_graphed_stacks_match_eager():
-    """accelerate(graph=True): the two stacks replayed from CUDA graphs inside the eager model give the eager result."""
+    """accelerate(graph=True): the two stacks replayed from CUDA graphs inside the eager model give the result of the
+    eager stacks (a second, identically initialised copy).  The graphs are built at the first forward, as in training."""
+    from d2r_b200.integration import accelerate
     ref, acc, synthetic_batch = _models()
+    eager = copy.deepcopy(ref)
     del ref
+    accelerate(eager)
+    acc.model.itr_module.__dict__["_d2r_graph"] = True
     batch = synthetic_batch(4, 32, seed=6, device="cuda")
-    acc.eval()
-    for mod in acc.modules():
-        if isinstance(mod, torch.nn.BatchNorm1d):
-            mod.train()
 
-    def run():
-        for p in acc.parameters():
+    def run(m):
+        m.eval()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.train()
+        for p in m.parameters():
             p.grad = None
-        bufs = [(b, b.detach().clone()) for b in acc.buffers()]
+        bufs = [(b, b.detach().clone()) for b in m.buffers()]
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss, logits = acc(*batch)
+            loss, logits = m(*batch)
         loss.backward()
         with torch.no_grad():
             for b, saved in bufs:
                 b.copy_(saved)
-        g = torch.cat([p.grad.flatten().float() for p in acc.parameters() if p.grad is not None])
+        g = torch.cat([p.grad.flatten().float() for p in m.parameters() if p.grad is not None])
         return loss.item(), logits.float().clone(), g
 
-    l0, lg0, g0 = run()
-    acc.model.itr_module.__dict__["_d2r_graph"] = True
-    for _ in range(2):                        # first call captures, second replays
-        l1, lg1, g1 = run()
+    for _ in range(3):                        # first call captures, the others replay
+        l1, lg1, g1 = run(acc)
+    l0, lg0, g0 = run(eager)
     assert abs(l1 - l0) <= 1e-3 * max(1.0, abs(l0))
     assert ((lg1 - lg0).abs().max() / lg0.abs().max()).item() <= 1e-3
     assert ((g1 - g0).norm() / g0.norm()).item() <= 2e-2       # atomically accumulated gradients differ in rounding
