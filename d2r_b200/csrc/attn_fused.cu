@@ -17,7 +17,8 @@
 //   warp 0      TMA producer: per unit the Q / K k-blocks of phase 1, then the V tiles of phase 2, through one ring
 //   warp 1      MMA issuer:   S(u+1) is issued BEFORE P V(u), so the softmax of unit u overlaps the next unit's
 //                             score product (two S accumulators, two P tiles, two O accumulators: 512 TMEM columns)
-//   warps 2..9  softmax + output epilogue (warp pair (q, half) shares TMEM lane quarter q, half = column half)
+//   warps 2..5  softmax (one thread per score row: TMEM -> registers -> bf16 P tile in shared memory + TMA store of P)
+//   warps 6..9  output epilogue (P V accumulator tiles -> (+ residual | squared difference) -> TMA store)
 // Barriers: full/empty[stage] (TMA <-> MMA), s_full/s_free[2] (MMA <-> softmax), p_ready[2] (softmax -> MMA),
 //           o_full/o_empty[2] (MMA <-> output epilogue).
 #include <cuda.h>
@@ -115,10 +116,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&s_full[a], 1);
-      mbar_init(&s_free[a], 8);
-      mbar_init(&p_ready[a], 8);
+      mbar_init(&s_free[a], 4);                 // the four softmax warps
+      mbar_init(&p_ready[a], 4);
       mbar_init(&o_full[a], 1);
-      mbar_init(&o_empty[a], 8);
+      mbar_init(&o_empty[a], 4);                // the four output warps
     }
     fence_barrier_init();
   }
@@ -246,149 +247,145 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------- softmax + output epilogue
+    // ------------------------------------------------------------- softmax warps (2..5) / output warps (6..9)
+    // Each group of four warps covers the four TMEM lane quarters.  The softmax of unit i+1 therefore runs WHILE the
+    // output tiles of unit i are drained (first version: all eight warps did both, one after the other, and the
+    // per-unit chain softmax -> 6 x (PV tile -> epilogue) was serial on every warp).
     const int q = warp & 3;                     // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;           // which half of the columns
+    const bool softmax_role = warp < 6;
     const int ew = warp - 2;
-    uint8_t* stg = store_stage + ew * 2048;
-    float* xch_mine = xch + ew * 128;
-    const float* xch_peer = xch + (half == 0 ? ew + 4 : ew - 4) * 128;
     const int r = q * 32 + lane;                // row of the unit's 128-row tile
-    int oc = 0;
-    for (int i = 0; i < n_mine; ++i) {
-      const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
-      const int sb = i & 1;
-      uint8_t* pb = pbuf + sb * Cfg::P_BYTES;
-      // ---- softmax of this warp pair's 32 rows; this warp owns CPW chunks of 32 columns
-      mbar_wait(&s_full[sb], static_cast<uint32_t>(i >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t ts = tmem_base + kColS + static_cast<uint32_t>(sb * 128) + (static_cast<uint32_t>(q * 32) << 16);
-      float e[CPW * 32];
-      float ml = -INFINITY;
-#pragma unroll
-      for (int cc = 0; cc < CPW; ++cc) {
-        const int c = half * CPW + cc;
-        uint32_t ra[32];
-        tmem_ld32(ts + c * 32, ra);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = (c * 32 + j < p.Lc) ? p.sc * __uint_as_float(ra[j]) : -INFINITY;
-          e[cc * 32 + j] = x;
-          ml = fmaxf(ml, x);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[sb]);  // the score accumulator may be overwritten (unit i + 2)
-      const float ms = ml == -INFINITY ? 0.f : ml;
-      float sl = 0.f;
-#pragma unroll
-      for (int j = 0; j < CPW * 32; ++j) {
-        e[j] = ex2_ftz(e[j] - ms);
-        sl += e[j];
-      }
-      *reinterpret_cast<float2*>(xch_mine + lane * 2) = make_float2(ml, sl);
-      // the bulk stores that read this P tile two units ago were issued by this lane: drained before anyone rewrites
-      if (half == 0 && lane == 0) bulk_wait_read0();
-      pair_barrier(q);
-      const float2 pp = *reinterpret_cast<const float2*>(xch_peer + lane * 2);
-      const float mx = fmaxf(ml, pp.x);
-      const float mine = ex2_ftz(ml - mx);
-      const float f = mine / (sl * mine + pp.y * ex2_ftz(pp.x - mx));
-#pragma unroll
-      for (int cc = 0; cc < CPW; ++cc) {
-        const int c = half * CPW + cc;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float t8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t8[j] = e[cc * 32 + g * 8 + j] * f;
-          const int col0 = c * 32 + g * 8;
-          const int unit16 = (col0 & 63) >> 3;
-          *reinterpret_cast<uint4*>(pb + (col0 >> 6) * kQTile + r * 128 + ((unit16 ^ (r & 7)) << 4)) = pack8_bf16(t8);
-        }
-      }
-      fence_proxy_async();                      // generic-proxy writes of P -> visible to tcgen05.mma / TMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[sb]);
-      pair_barrier(q);                          // both halves of this quarter's rows are in shared memory
-      if (half == 0 && lane == 0) {
-#pragma unroll
-        for (int a = 0; a < KCB; ++a)
-          tma_store_4d(&tmP, pb + a * kQTile + q * 32 * 128, a * 64, u.qt * 128 + q * 32, u.h, u.b);
-        bulk_commit();
-      }
-      // ---- output tiles of this unit
-      const int row0 = u.qt * 128 + q * 32;
-      const bool row_ok = row0 + lane < p.Lq;
-      const __nv_bfloat16* rrow = nullptr;
-      if (p.residual)
-        rrow = p.residual + static_cast<long long>(u.b) * p.r_sb + static_cast<long long>(u.h) * p.r_sh +
-               static_cast<long long>(row0 + lane) * p.r_ld;
-      const int nco = p.nt >> 5;                // 32-column chunks per output tile (2 | 4)
-      const int cpo = nco >> 1;
-      for (int t = 0; t < p.n_tiles; ++t) {
-        const int ob = oc & 1;
-        // The residual of this tile's chunks is fetched BEFORE waiting for the accumulator: eight independent 16-byte
-        // loads per thread in flight under the MMA wait.  (First version: one load at a time behind the wait, each
-        // followed by its unpack -- ncu showed 44 % of the kernel's stall samples on those four LDG.128.)
-        uint4 rr[2][4];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int col0 = t * p.nt + (half * cpo + cc) * 32;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            // hd is a multiple of 8: a group of 8 columns is entirely inside or outside the head
-            const bool ok = rrow != nullptr && cc < cpo && row_ok && col0 + g * 8 < p.hd;
-            rr[cc][g] = ok ? __ldg(reinterpret_cast<const uint4*>(rrow + col0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
+    if (softmax_role) {
+      for (int i = 0; i < n_mine; ++i) {
+        const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+        const int sb = i & 1;
+        uint8_t* pb = pbuf + sb * Cfg::P_BYTES;
+        mbar_wait(&s_full[sb], static_cast<uint32_t>(i >> 1) & 1u);
         tc_fence_after();
+        const uint32_t ts = tmem_base + kColS + static_cast<uint32_t>(sb * 128) + (static_cast<uint32_t>(q * 32) << 16);
+        float e[NCH * 32];                      // this thread's whole score row
+        float ml = -INFINITY;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          if (cc >= cpo) break;
-          const int c = half * cpo + cc;
-          const int col0 = t * p.nt + c * 32;   // column inside the head
-          if (col0 >= p.hd) continue;
+        for (int c = 0; c < NCH; ++c) {
           uint32_t ra[32];
-          float v[32], d[32];
-          tmem_ld32(tmem_base + kColO + static_cast<uint32_t>(ob * 128) + (static_cast<uint32_t>(q * 32) << 16) + c * 32, ra);
-          float res[32];
-          if (rrow != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rr[cc][g]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(hh[j]);
-                res[g * 8 + 2 * j] = f.x;
-                res[g * 8 + 2 * j + 1] = f.y;
-              }
-            }
-          }
+          tmem_ld32(ts + c * 32, ra);
           tmem_ld_wait();
-          if (p.mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              d[j] = res[j] - __uint_as_float(ra[j]);
-              v[j] = d[j] * d[j];
-            }
-            tma_store_row32<__nv_bfloat16>(&tmO2, stg, lane, d, col0, row0, u.h, u.b);
-          } else if (rrow != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + res[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+          for (int j = 0; j < 32; ++j) {
+            const float x = (c * 32 + j < p.Lc) ? p.sc * __uint_as_float(ra[j]) : -INFINITY;
+            e[c * 32 + j] = x;
+            ml = fmaxf(ml, x);
           }
-          tma_store_row32<__nv_bfloat16>(&tmO, stg, lane, v, col0, row0, u.h, u.b);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[ob]);
-        ++oc;
+        if (lane == 0) mbar_arrive(&s_free[sb]);  // the score accumulator may be overwritten (unit i + 2)
+        float sl = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH * 32; ++j) {
+          e[j] = ex2_ftz(e[j] - ml);              // Lc >= 1: the row maximum is finite
+          sl += e[j];
+        }
+        const float f = 1.f / sl;
+        // the bulk stores that read this warp's rows of this P tile two units ago were issued by this lane
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < NCH * 4; ++g) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t8[j] = e[g * 8 + j] * f;
+          const int col0 = g * 8;
+          *reinterpret_cast<uint4*>(pb + (col0 >> 6) * kQTile + r * 128 + ((((col0 & 63) >> 3) ^ (r & 7)) << 4)) =
+              pack8_bf16(t8);
+        }
+        fence_proxy_async();                      // generic-proxy writes of P -> visible to tcgen05.mma / TMA
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_ready[sb]);
+#pragma unroll
+          for (int a = 0; a < KCB; ++a)
+            tma_store_4d(&tmP, pb + a * kQTile + q * 32 * 128, a * 64, u.qt * 128 + q * 32, u.h, u.b);
+          bulk_commit();
+        }
+      }
+    } else {
+      uint8_t* stg = store_stage + ew * 2048;
+      int oc = 0;
+      const int nco = p.nt >> 5;                // 32-column chunks per output tile (2 | 4)
+      for (int i = 0; i < n_mine; ++i) {
+        const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+        const int row0 = u.qt * 128 + q * 32;
+        const bool row_ok = row0 + lane < p.Lq;
+        const __nv_bfloat16* rrow = nullptr;
+        if (p.residual)
+          rrow = p.residual + static_cast<long long>(u.b) * p.r_sb + static_cast<long long>(u.h) * p.r_sh +
+                 static_cast<long long>(row0 + lane) * p.r_ld;
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int ob = oc & 1;
+          for (int c0 = 0; c0 < nco; c0 += 2) {
+            // The residual of two chunks is fetched BEFORE the accumulator wait / while the previous pair drains:
+            // eight independent 16-byte loads per thread in flight.  (First version: one load at a time behind the
+            // wait, each followed by its unpack -- ncu showed 44 % of the stall samples on those LDG.128.)
+            uint4 rr[2][4];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int col0 = t * p.nt + (c0 + cc) * 32;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                // hd is a multiple of 8: a group of 8 columns is entirely inside or outside the head
+                const bool ok = rrow != nullptr && row_ok && col0 + g * 8 < p.hd;
+                rr[cc][g] = ok ? __ldg(reinterpret_cast<const uint4*>(rrow + col0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+            if (c0 == 0) {
+              mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = c0 + cc;
+              const int col0 = t * p.nt + c * 32;   // column inside the head
+              if (col0 >= p.hd) continue;
+              uint32_t ra[32];
+              float v[32], d[32];
+              tmem_ld32(tmem_base + kColO + static_cast<uint32_t>(ob * 128) + (static_cast<uint32_t>(q * 32) << 16) + c * 32, ra);
+              float res[32];
+              if (rrow != nullptr) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rr[cc][g]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 fl = __bfloat1622float2(hh[j]);
+                    res[g * 8 + 2 * j] = fl.x;
+                    res[g * 8 + 2 * j + 1] = fl.y;
+                  }
+                }
+              }
+              tmem_ld_wait();
+              if (p.mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  d[j] = res[j] - __uint_as_float(ra[j]);
+                  v[j] = d[j] * d[j];
+                }
+                tma_store_row32<__nv_bfloat16>(&tmO2, stg, lane, d, col0, row0, u.h, u.b);
+              } else if (rrow != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + res[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+              }
+              tma_store_row32<__nv_bfloat16>(&tmO, stg, lane, v, col0, row0, u.h, u.b);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty[ob]);
+          ++oc;
+        }
       }
     }
     if (lane == 0) bulk_wait_all();
