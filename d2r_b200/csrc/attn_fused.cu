@@ -47,10 +47,13 @@ struct AfCfg {
   static constexpr int STAGE_BYTES = kQTile + BNS * 128;            // Q k-block + K k-block (24 / 32 KB)
   static constexpr int STAGES = BNS == 64 ? 6 : 4;
   static constexpr int P_BYTES = (BNS / 64) * kQTile;               // one P tile [128 x BNS] bf16
-  static constexpr int STORE_BYTES = 8 * 2048;
+  static constexpr int STORE_BYTES = 8 * 4096;                      // one [32 x 128 B] staging tile per epilogue warp
   static constexpr int BAR_BYTES = 512;
-  static constexpr int XCH_BYTES = 8 * 128 * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * P_BYTES + STORE_BYTES + BAR_BYTES + XCH_BYTES + 1024;
+  static constexpr int XCH_BYTES = 8 * 64 * 4;                      // softmax statistics exchanged inside a warp pair
+  // no 1 KB alignment slack: the kernel declares its dynamic shared memory __align__(1024) (and traps if the base is
+  // not aligned); the 128-key configuration needs 226.5 KB of the 227 KB a CTA may have
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * P_BYTES + STORE_BYTES + BAR_BYTES + XCH_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "attn_fwd: shared memory budget");
 };
 
 struct AfParams {
@@ -76,7 +79,10 @@ __device__ __forceinline__ Unit decode_unit(const AfParams& p, int u) {
   return x;
 }
 
-template <int BNS>
+// SPLIT (small head dims, one output tile per unit): warps 2..5 do the softmax, warps 6..9 the output tiles, so the
+// softmax of unit i+1 overlaps the output of unit i.  !SPLIT (head dim 768: six output tiles per unit, the output
+// dominates): all eight warps do both, a warp pair sharing a lane quarter splits the columns.
+template <int BNS, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP,
@@ -84,12 +90,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   using Cfg = AfCfg<BNS>;
   constexpr int KCB = BNS / 64;        // 64-key blocks of the P V product
   constexpr int NCH = BNS / 32;        // 32-column chunks of a score row
-  constexpr int CPW = NCH / 2;         // chunks per warp of a pair
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int CPW = NCH / 2;         // chunks per warp of a pair (!SPLIT)
+  constexpr int kArrive = SPLIT ? 4 : 8;   // warps that consume a score / output accumulator
+  extern __shared__ __align__(1024) uint8_t smem_fwd[];
+  if (smem_u32(smem_fwd) & 1023u) __trap();   // 128B-swizzled tiles must start on a 1024-byte boundary
+  uint8_t* smem = smem_fwd;
   uint8_t* pbuf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;            // 2 x P_BYTES, 1024-aligned
-  uint8_t* store_stage = pbuf + 2 * Cfg::P_BYTES;                   // [8][2048]
+  uint8_t* store_stage = pbuf + 2 * Cfg::P_BYTES;                   // [8][4096], 1024-aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* s_full = empty_bar + Cfg::STAGES;
@@ -98,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* o_full = p_ready + 2;
   uint64_t* o_empty = o_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
-  float* xch = reinterpret_cast<float*>(store_stage + Cfg::STORE_BYTES + Cfg::BAR_BYTES);   // [8][128]
+  float* xch = reinterpret_cast<float*>(store_stage + Cfg::STORE_BYTES + Cfg::BAR_BYTES);   // [8][64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,10 +123,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&s_full[a], 1);
-      mbar_init(&s_free[a], 4);                 // the four softmax warps
-      mbar_init(&p_ready[a], 4);
+      mbar_init(&s_free[a], kArrive);
+      mbar_init(&p_ready[a], kArrive);
       mbar_init(&o_full[a], 1);
-      mbar_init(&o_empty[a], 4);                // the four output warps
+      mbar_init(&o_empty[a], kArrive);
     }
     fence_barrier_init();
   }
@@ -247,145 +254,226 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------- softmax warps (2..5) / output warps (6..9)
-    // Each group of four warps covers the four TMEM lane quarters.  The softmax of unit i+1 therefore runs WHILE the
-    // output tiles of unit i are drained (first version: all eight warps did both, one after the other, and the
-    // per-unit chain softmax -> 6 x (PV tile -> epilogue) was serial on every warp).
+    // ------------------------------------------------------------- softmax + output epilogue (warps 2..9)
     const int q = warp & 3;                     // TMEM lane quarter of this warp
-    const bool softmax_role = warp < 6;
     const int ew = warp - 2;
+    const int half = ew >> 2;                   // SPLIT: 0 = softmax warp, 1 = output warp; else column half of the pair
     const int r = q * 32 + lane;                // row of the unit's 128-row tile
-    if (softmax_role) {
+    uint8_t* stg = store_stage + ew * 4096;
+    int oc = 0;
+
+    // output tiles of one unit: this warp drains 64-column chunk pairs [pair0, pair0 + npairs) of every tile
+    auto out_tiles = [&](const Unit& u, int pair0, int npairs) {
+      const int row0 = u.qt * 128 + q * 32;
+      const bool row_ok = row0 + lane < p.Lq;
+      const __nv_bfloat16* rrow = nullptr;
+      if (p.residual)
+        rrow = p.residual + static_cast<long long>(u.b) * p.r_sb + static_cast<long long>(u.h) * p.r_sh +
+               static_cast<long long>(row0 + lane) * p.r_ld;
+      for (int t = 0; t < p.n_tiles; ++t) {
+        const int ob = oc & 1;
+        for (int pi = 0; pi < npairs; ++pi) {
+          const int c0 = (pair0 + pi) * 2;
+          // The residual of the pair is fetched BEFORE the accumulator wait / while the previous pair drains: eight
+          // independent 16-byte loads per thread in flight.  (First version: one load at a time behind the wait,
+          // each followed by its unpack -- ncu showed 44 % of the stall samples on those LDG.128.)
+          uint4 rr[2][4];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int col0 = t * p.nt + (c0 + cc) * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              // hd is a multiple of 8: a group of 8 columns is entirely inside or outside the head
+              const bool ok = rrow != nullptr && row_ok && col0 + g * 8 < p.hd;
+              rr[cc][g] = ok ? __ldg(reinterpret_cast<const uint4*>(rrow + col0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          if (pi == 0) {
+            mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
+            tc_fence_after();
+          }
+          const int colp = t * p.nt + c0 * 32;      // first column of the pair inside the head
+          if (colp >= p.hd) continue;
+          // one pass per output tensor (the squared-difference epilogue writes d and d*d): chunk by chunk from TMEM
+          // into the 128B-swizzled staging tile, then ONE 64-column TMA store
+          const int npass = p.mode == 1 ? 2 : 1;
+          for (int pass = 0; pass < npass; ++pass) {
+            if (lane == 0) bulk_wait_read0();       // the previous store has finished reading the staging tile
+            __syncwarp();
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t ra[32];
+              tmem_ld32(tmem_base + kColO + static_cast<uint32_t>(ob * 128) + (static_cast<uint32_t>(q * 32) << 16) +
+                            (c0 + cc) * 32, ra);
+              tmem_ld_wait();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rr[cc][g]);
+                float t8[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 fl = __bfloat1622float2(hh[j]);          // (zero without residual)
+                  const float a0 = __uint_as_float(ra[g * 8 + 2 * j]), a1 = __uint_as_float(ra[g * 8 + 2 * j + 1]);
+                  if (p.mode == 1) {
+                    const float d0 = fl.x - a0, d1 = fl.y - a1;
+                    t8[2 * j] = pass == 0 ? d0 : d0 * d0;
+                    t8[2 * j + 1] = pass == 0 ? d1 : d1 * d1;
+                  } else {
+                    t8[2 * j] = a0 + fl.x;
+                    t8[2 * j + 1] = a1 + fl.y;
+                  }
+                }
+                *reinterpret_cast<uint4*>(stg + lane * 128 + (((cc * 4 + g) ^ (lane & 7)) << 4)) = pack8_bf16(t8);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d((p.mode == 1 && pass == 0) ? &tmO2 : &tmO, stg, colp, row0, u.h, u.b);
+              bulk_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[ob]);
+        ++oc;
+      }
+    };
+
+    if constexpr (SPLIT) {
+      if (half == 0) {
+        // ---- softmax warps: one thread per score row
+        for (int i = 0; i < n_mine; ++i) {
+          const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+          const int sb = i & 1;
+          uint8_t* pb = pbuf + sb * Cfg::P_BYTES;
+          mbar_wait(&s_full[sb], static_cast<uint32_t>(i >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t ts = tmem_base + kColS + static_cast<uint32_t>(sb * 128) + (static_cast<uint32_t>(q * 32) << 16);
+          float e[NCH * 32];
+          float ml = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t ra[32];
+            tmem_ld32(ts + c * 32, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = (c * 32 + j < p.Lc) ? p.sc * __uint_as_float(ra[j]) : -INFINITY;
+              e[c * 32 + j] = x;
+              ml = fmaxf(ml, x);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[sb]);  // the score accumulator may be overwritten (unit i + 2)
+          float sl = 0.f;
+#pragma unroll
+          for (int j = 0; j < NCH * 32; ++j) {
+            e[j] = ex2_ftz(e[j] - ml);              // Lc >= 1: the row maximum is finite
+            sl += e[j];
+          }
+          const float f = 1.f / sl;
+          // the bulk stores that read this warp's rows of this P tile two units ago were issued by this lane
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < NCH * 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = e[g * 8 + j] * f;
+            const int col0 = g * 8;
+            *reinterpret_cast<uint4*>(pb + (col0 >> 6) * kQTile + r * 128 + ((((col0 & 63) >> 3) ^ (r & 7)) << 4)) =
+                pack8_bf16(t8);
+          }
+          fence_proxy_async();                      // generic-proxy writes of P -> visible to tcgen05.mma / TMA
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&p_ready[sb]);
+#pragma unroll
+            for (int a = 0; a < KCB; ++a)
+              tma_store_4d(&tmP, pb + a * kQTile + q * 32 * 128, a * 64, u.qt * 128 + q * 32, u.h, u.b);
+            bulk_commit();
+          }
+        }
+      } else {
+        // ---- output warps
+        for (int i = 0; i < n_mine; ++i) {
+          const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
+          out_tiles(u, 0, p.nt >> 6);
+        }
+      }
+    } else {
+      float* xch_mine = xch + ew * 64;
+      const float* xch_peer = xch + (half == 0 ? ew + 4 : ew - 4) * 64;
       for (int i = 0; i < n_mine; ++i) {
         const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
         const int sb = i & 1;
         uint8_t* pb = pbuf + sb * Cfg::P_BYTES;
+        // ---- softmax of this warp pair's 32 rows; this warp owns CPW chunks of 32 columns
         mbar_wait(&s_full[sb], static_cast<uint32_t>(i >> 1) & 1u);
         tc_fence_after();
         const uint32_t ts = tmem_base + kColS + static_cast<uint32_t>(sb * 128) + (static_cast<uint32_t>(q * 32) << 16);
-        float e[NCH * 32];                      // this thread's whole score row
+        float e[CPW * 32];
         float ml = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int cc = 0; cc < CPW; ++cc) {
+          const int c = half * CPW + cc;
           uint32_t ra[32];
           tmem_ld32(ts + c * 32, ra);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float x = (c * 32 + j < p.Lc) ? p.sc * __uint_as_float(ra[j]) : -INFINITY;
-            e[c * 32 + j] = x;
+            e[cc * 32 + j] = x;
             ml = fmaxf(ml, x);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[sb]);  // the score accumulator may be overwritten (unit i + 2)
+        const float ms = ml == -INFINITY ? 0.f : ml;
         float sl = 0.f;
 #pragma unroll
-        for (int j = 0; j < NCH * 32; ++j) {
-          e[j] = ex2_ftz(e[j] - ml);              // Lc >= 1: the row maximum is finite
+        for (int j = 0; j < CPW * 32; ++j) {
+          e[j] = ex2_ftz(e[j] - ms);
           sl += e[j];
         }
-        const float f = 1.f / sl;
-        // the bulk stores that read this warp's rows of this P tile two units ago were issued by this lane
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
+        *reinterpret_cast<float2*>(xch_mine + lane * 2) = make_float2(ml, sl);
+        // the bulk stores that read this P tile two units ago were issued by this lane: drained before anyone rewrites
+        if (half == 0 && lane == 0) bulk_wait_read0();
+        pair_barrier(q);
+        const float2 pp = *reinterpret_cast<const float2*>(xch_peer + lane * 2);
+        const float mx = fmaxf(ml, pp.x);
+        const float mine = ex2_ftz(ml - mx);
+        const float f = mine / (sl * mine + pp.y * ex2_ftz(pp.x - mx));
 #pragma unroll
-        for (int g = 0; g < NCH * 4; ++g) {
-          float t8[8];
+        for (int cc = 0; cc < CPW; ++cc) {
+          const int c = half * CPW + cc;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t8[j] = e[g * 8 + j] * f;
-          const int col0 = g * 8;
-          *reinterpret_cast<uint4*>(pb + (col0 >> 6) * kQTile + r * 128 + ((((col0 & 63) >> 3) ^ (r & 7)) << 4)) =
-              pack8_bf16(t8);
+          for (int g = 0; g < 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = e[cc * 32 + g * 8 + j] * f;
+            const int col0 = c * 32 + g * 8;
+            const int unit16 = (col0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(pb + (col0 >> 6) * kQTile + r * 128 + ((unit16 ^ (r & 7)) << 4)) = pack8_bf16(t8);
+          }
         }
         fence_proxy_async();                      // generic-proxy writes of P -> visible to tcgen05.mma / TMA
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&p_ready[sb]);
+        if (lane == 0) mbar_arrive(&p_ready[sb]);
+        pair_barrier(q);                          // both halves of this quarter's rows are in shared memory
+        if (half == 0 && lane == 0) {
 #pragma unroll
           for (int a = 0; a < KCB; ++a)
             tma_store_4d(&tmP, pb + a * kQTile + q * 32 * 128, a * 64, u.qt * 128 + q * 32, u.h, u.b);
           bulk_commit();
         }
-      }
-    } else {
-      uint8_t* stg = store_stage + ew * 2048;
-      int oc = 0;
-      const int nco = p.nt >> 5;                // 32-column chunks per output tile (2 | 4)
-      for (int i = 0; i < n_mine; ++i) {
-        const Unit u = decode_unit(p, (int)blockIdx.x + i * (int)gridDim.x);
-        const int row0 = u.qt * 128 + q * 32;
-        const bool row_ok = row0 + lane < p.Lq;
-        const __nv_bfloat16* rrow = nullptr;
-        if (p.residual)
-          rrow = p.residual + static_cast<long long>(u.b) * p.r_sb + static_cast<long long>(u.h) * p.r_sh +
-                 static_cast<long long>(row0 + lane) * p.r_ld;
-        for (int t = 0; t < p.n_tiles; ++t) {
-          const int ob = oc & 1;
-          for (int c0 = 0; c0 < nco; c0 += 2) {
-            // The residual of two chunks is fetched BEFORE the accumulator wait / while the previous pair drains:
-            // eight independent 16-byte loads per thread in flight.  (First version: one load at a time behind the
-            // wait, each followed by its unpack -- ncu showed 44 % of the stall samples on those LDG.128.)
-            uint4 rr[2][4];
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int col0 = t * p.nt + (c0 + cc) * 32;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                // hd is a multiple of 8: a group of 8 columns is entirely inside or outside the head
-                const bool ok = rrow != nullptr && row_ok && col0 + g * 8 < p.hd;
-                rr[cc][g] = ok ? __ldg(reinterpret_cast<const uint4*>(rrow + col0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
-              }
-            }
-            if (c0 == 0) {
-              mbar_wait(&o_full[ob], static_cast<uint32_t>(oc >> 1) & 1u);
-              tc_fence_after();
-            }
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int c = c0 + cc;
-              const int col0 = t * p.nt + c * 32;   // column inside the head
-              if (col0 >= p.hd) continue;
-              uint32_t ra[32];
-              float v[32], d[32];
-              tmem_ld32(tmem_base + kColO + static_cast<uint32_t>(ob * 128) + (static_cast<uint32_t>(q * 32) << 16) + c * 32, ra);
-              float res[32];
-              if (rrow != nullptr) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rr[cc][g]);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 fl = __bfloat1622float2(hh[j]);
-                    res[g * 8 + 2 * j] = fl.x;
-                    res[g * 8 + 2 * j + 1] = fl.y;
-                  }
-                }
-              }
-              tmem_ld_wait();
-              if (p.mode == 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  d[j] = res[j] - __uint_as_float(ra[j]);
-                  v[j] = d[j] * d[j];
-                }
-                tma_store_row32<__nv_bfloat16>(&tmO2, stg, lane, d, col0, row0, u.h, u.b);
-              } else if (rrow != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + res[j];
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-              }
-              tma_store_row32<__nv_bfloat16>(&tmO, stg, lane, v, col0, row0, u.h, u.b);
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&o_empty[ob]);
-          ++oc;
-        }
+        // ---- output tiles: each warp of the pair drains one 64-column half of every 128-column tile
+        //      (64-column tiles, i.e. small heads, always take the SPLIT kernel)
+        out_tiles(u, half, 1);
       }
     }
     if (lane == 0) bulk_wait_all();
@@ -400,11 +488,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int BNS>
+template <int BNS, bool SPLIT>
 int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmP,
                     const CUtensorMap& tmO, const CUtensorMap& tmO2, const AfParams& p, cudaStream_t stream) {
   using Cfg = AfCfg<BNS>;
-  auto kern = attn_fwd_kernel<BNS>;
+  auto kern = attn_fwd_kernel<BNS, SPLIT>;
   static std::atomic<int> attr_set[kMaxDevices];
   const int dev = current_device();
   if (!attr_set[dev].load(std::memory_order_acquire)) {
@@ -828,13 +916,17 @@ int d2r_attn_fwd(const d2r_attn_args* a, void* stream) {
   // P [B, heads, Lq, p_ld]: stored straight from the swizzled shared-memory tile, 32 rows x 64 columns per store
   if ((rc = encode_map(&tmP, a->p, 2, a->Lc, a->Lq, H, B, a->p_ld, (long long)a->Lq * a->p_ld,
                        H * a->Lq * a->p_ld, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = encode_map(&tmO, a->out, 2, a->hd, a->Lq, H, B, a->o_ld, a->hd, (long long)a->Lq * a->o_ld, 32, 32,
-                       CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  // outputs: 64 columns x 32 rows per store, straight from a 128B-swizzled staging tile
+  if ((rc = encode_map(&tmO, a->out, 2, a->hd, a->Lq, H, B, a->o_ld, a->hd, (long long)a->Lq * a->o_ld, 64, 32,
+                       CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if (a->mode == 1 &&
-      (rc = encode_map(&tmO2, a->out2, 2, a->hd, a->Lq, H, B, a->o_ld, a->hd, (long long)a->Lq * a->o_ld, 32, 32,
-                       CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if (bns == 64) return launch_attn_fwd<64>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
-  return launch_attn_fwd<128>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
+      (rc = encode_map(&tmO2, a->out2, 2, a->hd, a->Lq, H, B, a->o_ld, a->hd, (long long)a->Lq * a->o_ld, 64, 32,
+                       CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const bool split = p.nt == 64;          // small heads: one 64-column output tile per unit
+  if (bns == 64) return split ? launch_attn_fwd<64, true>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st)
+                              : launch_attn_fwd<64, false>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
+  return split ? launch_attn_fwd<128, true>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st)
+               : launch_attn_fwd<128, false>(tmQ, tmK, tmV, tmP, tmO, tmO2, p, st);
 }
 
 int d2r_attn_bwd(const d2r_attn_bwd_args* a, void* stream) {
