@@ -510,7 +510,7 @@ def full_arm(args):
     import torch.distributed as dist
     from baseline.full_model import build_reference_model, synthetic_batch
     from d2r_b200 import kernels as K
-    from d2r_b200.dp import FlatGradReducer
+    from d2r_b200.dp import BucketedGradReducer
     from d2r_b200.integration import accelerate
     cfg = CONFIGS["full"]
     rank = int(os.environ.get("RANK", "0"))
@@ -576,7 +576,6 @@ def full_arm(args):
         except Exception as e:
             stock = {"value": None, "unavailable": f"{type(e).__name__}: {e}"}
     accelerate(model, graph=not args.no_graph)
-    reducer = FlatGradReducer(model.parameters())
     graphed = not args.no_graph
     try:
         fwd_bwd(devb)                 # first call builds the CUDA graphs of the two stacks
@@ -586,14 +585,26 @@ def full_arm(args):
         torch.cuda.synchronize()
         model.model.itr_module.__dict__["_d2r_graph"] = False
         graphed = False
+        fwd_bwd(devb)
+        torch.cuda.synchronize()
+    # gradients live in one flat buffer from here on; its buckets are all-reduced from inside the backward
+    reducer = BucketedGradReducer(model.parameters(), bucket_mb=128.0)
+    reducer.plan()
     h_loss = torch.empty(1).pin_memory()
+
+    def fwd_bwd_dp(batch):
+        reducer.begin_step()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, logits = model(*batch)
+        loss.backward()
+        reducer.finish()
+        return loss
 
     def step(from_host=False):
         if from_host:
             for d, h in zip(devb, host):
                 d.copy_(h, non_blocking=True)
-        loss = fwd_bwd(devb)
-        reducer.step()
+        loss = fwd_bwd_dp(devb)
         if from_host:
             h_loss.copy_(loss.detach().float().reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -611,6 +622,7 @@ def full_arm(args):
     ms_e2e = time_steps(lambda: step(True), args.steps, 2)
     # share of the routed stacks in the step: the two stacks alone, same batch, same precision
     ms_stack = None
+    reducer.remove()                  # (no collectives from the rank-0-only measurement below)
     if rank == 0:
         bb = model.model
         t_in = torch.randn(B, cfg["Lt"], D, device=dev, requires_grad=True)
@@ -643,7 +655,8 @@ def full_arm(args):
             "dtype": "bf16", "data": "synthetic", "config": workload_config("full", world, B),
             "engine": {"cuda_graph": "the two stacks (forward graph + backward graph); encoders eager" if graphed else False,
                        "swap": "d2r_b200.integration.accelerate (stacks via run_pair, CLS poolers, Block fusion, js_div)",
-                       "allreduce": f"one flat fp32 bucket per step, {reducer.dead} never-used tensors excluded",
+                       "allreduce": f"{len(reducer.buckets)} buckets of one flat fp32 gradient buffer, all-reduced from "
+                                    f"inside the backward; {reducer.dead} never-used tensors excluded",
                        "parameters_M": nparams / 1e6},
             "clocks": clocks,
             "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",

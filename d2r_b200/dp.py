@@ -235,6 +235,98 @@ class FlatGradReducer:
         self.finish()
 
 
+class BucketedGradReducer:
+    """Whole-model data parallelism with the gradient all-reduce OVERLAPPED with the backward (what DDP does, with a
+    static plan instead of an unused-parameter search).
+
+    After one ordinary backward (``plan()``: the live set is whatever received a gradient -- 1074 of the 1184 tensors
+    of UnimoModelF), every live ``p.grad`` becomes a VIEW of one flat fp32 buffer; autograd accumulates into the views
+    in place, so no packing copy exists.  The buffer is cut into buckets of about ``bucket_mb`` in reverse parameter
+    order -- the order in which gradients become final -- and a post-accumulate hook launches a bucket's asynchronous
+    mean all-reduce (NCCL over NVLink) the moment its last gradient has landed, under the rest of the backward.
+
+        red = BucketedGradReducer(model.parameters()); loss.backward(); red.plan()       # once
+        for batch in data:
+            red.begin_step()            # zero the flat buffer (p.grad stay views of it)
+            loss = model(batch); loss.backward()
+            red.finish()                # join the bucket collectives; p.grad now hold the rank-mean
+            optimizer.step()
+    One backward per step (no gradient accumulation over micro-batches: a bucket is reduced when its parameters have
+    been written once)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 128.0,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.all_params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.params: List[torch.nn.Parameter] = []
+        self.flat: Optional[torch.Tensor] = None
+        self.buckets: List[list] = []          # [first element, end element, parameters in the bucket]
+        self._pending: List[int] = []
+        self._works: list = []
+        self._hooks: list = []
+
+    @property
+    def dead(self) -> int:
+        return len(self.all_params) - len(self.params)
+
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def plan(self) -> None:
+        live = [p for p in self.all_params if p.grad is not None]
+        if not live:
+            raise RuntimeError("BucketedGradReducer.plan(): call after a backward")
+        self.params = list(reversed(live))                      # roughly the order gradients are produced in
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
+        off = 0
+        cur = [0, 0, 0]
+        index = {}
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            if cur[2] and off - cur[0] >= self.bucket_elems:
+                cur[1] = off
+                self.buckets.append(cur)
+                cur = [off, 0, 0]
+            index[p] = len(self.buckets)
+            cur[2] += 1
+            off += p.numel()
+        cur[1] = off
+        self.buckets.append(cur)
+        self._pending = [b[2] for b in self.buckets]
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(
+                lambda _p, _b=index[p]: self._landed(_b)))
+
+    def _landed(self, b: int) -> None:
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self._distributed():
+            lo, hi, _ = self.buckets[b]
+            t = self.flat[lo:hi]
+            op = dist.ReduceOp.AVG if t.is_cuda else dist.ReduceOp.SUM
+            self._works.append((dist.all_reduce(t, op=op, group=self.group, async_op=True), t))
+
+    def begin_step(self) -> None:
+        self.flat.zero_()
+        self._pending = [b[2] for b in self.buckets]
+        self._works = []
+
+    def finish(self) -> None:
+        if any(self._pending) and self._distributed():
+            raise RuntimeError("BucketedGradReducer.finish(): some planned parameters received no gradient this step")
+        for w, t in self._works:
+            w.wait()
+            if not t.is_cuda:
+                t.div_(dist.get_world_size(self.group))          # gloo has no AVG
+        self._works = []
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 class InputPrefetcher:
     """Host -> device input pipeline of one rank: the pinned host batch of step i+1 is copied to the GPU on a copy
     stream while step i computes, then moved into the (static, CUDA-graph visible) input tensors with a

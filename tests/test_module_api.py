@@ -241,3 +241,58 @@ def test_lanes_degrade_to_one_stream_off_cuda():
         lanes.catch_up(2)
         lanes.wait_mark(lanes.mark(4))
         lanes.join()
+
+
+def _dp_bucketed_worker(rank, world, port, q):
+    """BucketedGradReducer on a small model with a never-used parameter: p.grad become views of one flat buffer, the
+    buckets are reduced from inside the backward, every rank ends with the mean of the per-rank gradients."""
+    import torch.distributed as dist
+    from d2r_b200.dp import BucketedGradReducer
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                torch.nn.Linear(16, 3))
+    unused = torch.nn.Parameter(torch.zeros(5))
+    params = list(model.parameters()) + [unused]
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    lo, hi = rank * 4, rank * 4 + 4
+    model(x[lo:hi]).pow(2).mean().backward()
+    red = BucketedGradReducer(params, bucket_mb=16 * 16 * 4 / (1 << 20))      # several buckets
+    red.plan()
+    assert red.dead == 1 and len(red.buckets) >= 2
+    for _ in range(2):                                                          # two steps: buffers are reused
+        red.begin_step()
+        model(x[lo:hi]).pow(2).mean().backward()
+        red.finish()
+    lo_ptr, hi_ptr = red.flat.data_ptr(), red.flat.data_ptr() + red.flat.numel() * 4
+    assert all(lo_ptr <= p.grad.data_ptr() < hi_ptr for p in model.parameters()) and unused.grad is None
+    q.put((rank, [p.grad.clone() for p in model.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_bucketed_overlapped_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_bucketed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                torch.nn.Linear(16, 3))
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    gs = []
+    for lo, hi in ((0, 4), (4, 8)):
+        model.zero_grad()
+        model(x[lo:hi]).pow(2).mean().backward()
+        gs.append([p.grad.clone() for p in model.parameters()])
+    for a, b, g0, g1 in zip(res[0][1], res[1][1], gs[0], gs[1]):
+        assert torch.equal(a, b)
+        torch.testing.assert_close(a, (g0 + g1) / 2)
