@@ -303,7 +303,7 @@ def own_arm(args):
         d_image.copy_(h_image)
 
     # gradient all-reduce: layer-wise, launched from inside the backward (overlapped), or one collective per step
-    overlap = args.overlap_allreduce
+    overlap = (args.overlap_allreduce or world > 1) and not args.no_overlap_allreduce
     if overlap:
         reducer.install()
 
@@ -952,8 +952,10 @@ def main():
     ap.add_argument("--serial-branches", action="store_true",
                     help="call the two branch modules back to back instead of run_pair (two CUDA streams)")
     ap.add_argument("--overlap-allreduce", action="store_true",
-                    help="layer-wise gradient all-reduces launched from inside the backward (GradAllReducer.install) "
-                         "instead of one collective after it")
+                    help="(default when N > 1) layer-wise gradient all-reduces launched from inside the backward "
+                         "(GradAllReducer.install), captured in the CUDA graph")
+    ap.add_argument("--no-overlap-allreduce", action="store_true",
+                    help="one gradient all-reduce per step, issued after the graph replay (round-1 behaviour)")
     ap.add_argument("--aux-wgrad", action="store_true", help="weight-gradient GEMMs on the helper stream as well")
     ap.add_argument("--no-aux-bias", action="store_true",
                     help="bias-gradient column sums on the GEMMs' own stream instead of a helper stream")
