@@ -39,22 +39,7 @@ def _stager_of(module: torch.nn.Module) -> S.Stager:
     return st
 
 
-def _to_compute(t: Tensor, cd: torch.dtype, cache: Optional[dict]) -> Tensor:
-    """Contiguous copy of an input in the compute dtype (library cast kernel).  ``cache``: conversions already made
-    by this call -- under run_pair both stacks take the same text and image tensors, which are cast once."""
-    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, cd)
-    if cache is not None and key in cache:
-        return cache[key]
-    x = t.detach()
-    if x.dtype != cd:
-        x = K.cast(x, cd) if x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) else x.to(cd)
-    x = x.contiguous()
-    if cache is not None:
-        cache[key] = x
-    return x
-
-
-def _fwd_one(spec, tensors, converted=None):
+def _fwd_one(spec, tensors):
     """Run one block's forward on the CURRENT stream -> (outs, record for the backward)."""
     n_in, names, bufs, fwd, bwd, cd, training, stager, heads, out_nondiff = spec[:10]
     inputs = tensors[:n_in]
@@ -62,7 +47,7 @@ def _fwd_one(spec, tensors, converted=None):
     P.update(bufs)
     env = S.Env(P, cd, training, stager, heads)
     env.layer_hook = spec[10]
-    x_cd = [None if t is None else _to_compute(t, cd, converted) for t in inputs]
+    x_cd = [None if t is None else t.detach().to(cd).contiguous() for t in inputs]
     outs, state = fwd(env, x_cd)
     rec = dict(spec=spec, state=state, in_dtypes=[None if t is None else t.dtype for t in inputs],
                out_meta=[(o.shape, o.dtype) for o in outs])
@@ -112,22 +97,12 @@ class _BlocksFn(torch.autograd.Function):
         # every launch, stream lookup and allocation below refers to the operands' device, whatever the caller's
         # current device is (the C ABI launches on the stream it is handed and never calls cudaSetDevice)
         with _device_guard(dev):
-            # inputs shared by several blocks (run_pair: text and image feed both stacks) are cast once, on the
-            # caller's stream, BEFORE the lanes fork from it
-            converted: dict = {}
-            if len(specs) > 1:
-                off = 0
-                for spec in specs:
-                    for t in tensors[off:off + spec[0]]:
-                        if t is not None:
-                            _to_compute(t, spec[5], converted)
-                    off += spec[0] + len(spec[1])
             lanes, first = _block_lanes(dev, len(specs))
             recs, all_outs, off = [], [], 0
             for i, spec in enumerate(specs):
                 n = spec[0] + len(spec[1])
                 with lanes.lane(first + i):
-                    outs, rec = _fwd_one(spec, tensors[off:off + n], converted)
+                    outs, rec = _fwd_one(spec, tensors[off:off + n])
                 off += n
                 recs.append(rec)
                 all_outs.append(outs)
