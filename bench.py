@@ -208,6 +208,8 @@ def reference_arm(args):
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "CPU arm: `config` names the workload of the GPU arm; each timed step here is a bounded batch-8 sample of "
+                "it (cpu_baseline.sample), run by rank 0 only on the host cores",
     }
     emit(line)
     return 0

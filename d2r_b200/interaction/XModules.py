@@ -1,8 +1,9 @@
 """Mirror of the live parts of reference models/XModules.py: l1norm/l2norm :14-24, CrossModalAlignment
 :277-328 (live part :300-310; the reverse-attention / ContrastiveLoss branch :312-326 is dead work whose
 result every caller discards -- its parameters fc_1/fc_2 are kept for state_dict parity, the returned
-loss is a constant 0), AttentionFiltration :366-394, js_div :32-41 (fused kernel).  ``Block`` (used by the
-backbone after the stack) is not mirrored yet."""
+loss is a constant 0), AttentionFiltration :366-394, js_div :32-41 (fused kernel).  ``Block`` :478-555 (the
+bilinear fusion the backbone applies after the stack, SURVEY §8f: batched merge GEMMs + one fused rank-sum /
+signed-sqrt / normalise kernel)."""
 import math
 
 import numpy as np
