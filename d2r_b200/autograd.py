@@ -47,6 +47,7 @@ def _fwd_one(spec, tensors):
     P.update(bufs)
     env = S.Env(P, cd, training, stager, heads)
     env.layer_hook = spec[10]
+    env.bn_modes = spec[11]
     x_cd = [None if t is None else t.detach().to(cd).contiguous() for t in inputs]
     outs, state = fwd(env, x_cd)
     rec = dict(spec=spec, state=state, in_dtypes=[None if t is None else t.dtype for t in inputs],
@@ -160,6 +161,17 @@ def _require_cuda(inputs) -> None:
                                "there is no CPU path")
 
 
+def _bn_modes(module: torch.nn.Module, prefix: str) -> Dict[str, bool]:
+    """Train/eval flag of every BatchNorm1d below ``module``, by prefixed name.  The reference's batch-norm layers each
+    read their OWN flag (XModules.py:380-384 calls ``self.bn``), so statistics frozen with ``bn.eval()`` under
+    ``model.train()`` -- or the reverse -- must behave the same here.  The module list is collected once."""
+    bns = module.__dict__.get("_d2r_bns")
+    if bns is None:
+        bns = [(n, m) for n, m in module.named_modules() if isinstance(m, torch.nn.BatchNorm1d)]
+        module.__dict__["_d2r_bns"] = bns
+    return {prefix + n: m.training for n, m in bns}
+
+
 def _make_spec(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]], fwd: Callable, bwd: Callable, *,
                prefix: str = "", cd: Optional[torch.dtype] = None, heads: int = 16,
                out_nondiff: Tuple[int, ...] = ()):
@@ -179,7 +191,7 @@ def _make_spec(module: torch.nn.Module, inputs: Sequence[Optional[Tensor]], fwd:
 
     # optional per-layer gradient callback (d2r_b200.dp.GradAllReducer.install): layer prefix, {name: grad}
     spec = (len(inputs), tuple(names), bufs, fwd_wrapped, bwd, cd, module.training, _stager_of(module), heads,
-            tuple(out_nondiff), module.__dict__.get("_d2r_layer_hook"))
+            tuple(out_nondiff), module.__dict__.get("_d2r_layer_hook"), _bn_modes(module, prefix))
     return spec, list(inputs) + params
 
 

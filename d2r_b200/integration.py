@@ -26,6 +26,7 @@ import sys
 import torch
 import torch.nn as nn
 
+from .autograd import _bn_modes
 from .interaction.Cells import BertPooler
 from .interaction.InteractionModule import InteractionModule, Reversed_InteractionModule, run_pair
 from .interaction.XModules import Block, js_div
@@ -72,7 +73,8 @@ class _PairedInteraction(InteractionModule):
         if (self.__dict__.get("_d2r_graph") and torch.is_grad_enabled() and text.requires_grad and image.requires_grad
                 and not torch.cuda.is_current_stream_capturing()):
             cache = self.__dict__.setdefault("_d2r_graph_cache", {})
-            key = (tuple(text.shape), tuple(image.shape), text.dtype, image.dtype, self.training,
+            key = (tuple(text.shape), tuple(image.shape), text.dtype, image.dtype, self.training, partner.training,
+                   tuple(_bn_modes(self, "").values()), tuple(_bn_modes(partner, "").values()),
                    torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda"))
             fn = cache.get(key)
             if fn is None:
@@ -110,6 +112,11 @@ def _rebind(new: nn.Module, old: nn.Module) -> nn.Module:
         sub = new.get_submodule(mod) if mod else new
         sub._buffers[leaf] = b
     new.train(old.training)
+    for name, m in old.named_modules():          # per-module flags (e.g. batch-norm layers frozen with .eval())
+        try:
+            new.get_submodule(name).training = m.training
+        except AttributeError:
+            pass
     return new
 
 

@@ -114,7 +114,7 @@ class AttentionFiltration(nn.Module):
             sg, sl = s[:, 0].contiguous(), s[:, 1:].contiguous()
             out, saved = K.saf_fwd(sg, sl, P["attn_sim_w.weight"].detach().view(-1), P["attn_sim_w.bias"].detach(),
                                    P["bn.weight"].detach(), P["bn.bias"].detach(), P["bn.running_mean"],
-                                   P["bn.running_var"], P.get("bn.num_batches_tracked"), env.training)
+                                   P["bn.running_var"], P.get("bn.num_batches_tracked"), env.bn_training("bn"))
             return (out,), dict(sg=sg, sl=sl, saved=saved)
 
         def bwd(env, st, grads):
@@ -122,7 +122,7 @@ class AttentionFiltration(nn.Module):
             d_sg, d_sl, d_w, d_b, d_bnw, d_bnb = K.saf_bwd(
                 grads[0], st["sg"], st["sl"], P["attn_sim_w.weight"].detach().view(-1), P["attn_sim_w.bias"].detach(),
                 P["bn.weight"].detach(), P["bn.bias"].detach(), P["bn.running_mean"], P["bn.running_var"],
-                env.training, st["saved"])
+                env.bn_training("bn"), st["saved"])
             env.grad("attn_sim_w.weight", d_w.view(1, -1))
             env.grad("attn_sim_w.bias", d_b)
             env.grad("bn.weight", d_bnw)

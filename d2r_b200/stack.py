@@ -86,12 +86,17 @@ class Env:
         self.P = params
         self.cd = cd
         self.training = training
+        self.bn_modes: Dict[str, bool] = {}   # BatchNorm1d name -> its own train/eval flag (autograd._bn_modes)
         self.st = stager
         self.layer_hook = None         # callable(layer prefix, {name: grad}) after each layer's backward
         self._fresh: set = set()       # staged-weight keys this call has already refreshed (see Stager)
         self._aux: Dict[int, tuple] = {}   # parent stream handle -> (parent, helper stream, tensors kept alive)
         self.heads = heads
         self.G: Dict[str, Tensor] = {}
+
+    def bn_training(self, name: str) -> bool:
+        """Does the batch-norm layer ``name`` use batch statistics?  (Its own flag, like nn.BatchNorm1d.forward.)"""
+        return self.bn_modes.get(name, self.training)
 
     @contextlib.contextmanager
     def aux(self, *keep: Tensor):
@@ -419,7 +424,7 @@ def _glac_saf_fwd(env: Env, c: str, sgc: Tensor, t2: Tensor):
     nbt = P.get(s + ".bn.num_batches_tracked")
     return K.saf_fwd(sgc, t2, P[s + ".attn_sim_w.weight"].detach().view(-1), P[s + ".attn_sim_w.bias"].detach(),
                      P[s + ".bn.weight"].detach(), P[s + ".bn.bias"].detach(), P[s + ".bn.running_mean"],
-                     P[s + ".bn.running_var"], nbt, env.training)
+                     P[s + ".bn.running_var"], nbt, env.bn_training(s + ".bn"))
 
 
 def _glac_fwd(env: Env, c: str, x: Tensor, z: Tensor, kv: _KV, ki: int):
@@ -438,7 +443,7 @@ def _glac_saf_bwd(env: Env, c: str, sv, d_out: Tensor):
     d_sgc, d_t2, d_w, d_b, d_bnw, d_bnb = K.saf_bwd(
         d_out, sv["sgc"], sv["t2"], P[s + ".attn_sim_w.weight"].detach().view(-1), P[s + ".attn_sim_w.bias"].detach(),
         P[s + ".bn.weight"].detach(), P[s + ".bn.bias"].detach(), P[s + ".bn.running_mean"],
-        P[s + ".bn.running_var"], env.training, sv["saf"])
+        P[s + ".bn.running_var"], env.bn_training(s + ".bn"), sv["saf"])
     env.grad(s + ".attn_sim_w.weight", d_w.view(1, -1))
     env.grad(s + ".attn_sim_w.bias", d_b)
     env.grad(s + ".bn.weight", d_bnw)
