@@ -63,8 +63,18 @@ def _graphed_pair(itr, rev, text, image):
     return fn
 
 
+def _portable_state(module: nn.Module) -> dict:
+    """Module state for pickling / deep-copying: captured CUDA graphs and a parked result stay behind."""
+    d = module.__dict__.copy()
+    d.pop("_d2r_graph_cache", None)
+    d.pop("_d2r_parked", None)
+    return d
+
+
 class _PairedInteraction(InteractionModule):
     """First of the two back-to-back stack calls: runs both stacks concurrently, parks the partner's result."""
+
+    __getstate__ = _portable_state
 
     def forward(self, text, image, return_path_probs=False):
         partner = self.__dict__.get("_d2r_partner")
@@ -88,6 +98,8 @@ class _PairedInteraction(InteractionModule):
 
 
 class _PairedReversedInteraction(Reversed_InteractionModule):
+    __getstate__ = _portable_state
+
     def forward(self, text, image, return_path_probs=False):
         parked = self.__dict__.pop("_d2r_parked", None)
         if parked is not None and not return_path_probs and parked[0] is text and parked[1] is image:

@@ -9,7 +9,7 @@ import torch.nn as nn
 from .. import kernels as K
 from .. import stack as S
 from ..autograd import run_block
-from .Refinement import Refinement, _bert_config
+from .Refinement import FallbackConfig, Refinement, _bert_config
 from .Router import Router
 from .SelfAttention import SelfAttention
 from .XModules import AttentionFiltration, CrossModalAlignment, hidden_size_of, l1norm, l2norm  # noqa: F401
@@ -20,9 +20,7 @@ def _clip_vision_config(name):
         from transformers import CLIPConfig
         return CLIPConfig.from_pretrained(name).vision_config
     except Exception:
-        class _Cfg:
-            hidden_size = 768
-        return _Cfg()
+        return FallbackConfig()
 
 
 def _route(env, x, router_prefix):

@@ -6,15 +6,18 @@ from ..autograd import run_block
 from .XModules import hidden_size_of, _cma_block
 
 
+class FallbackConfig:
+    """Stand-in for a Hugging Face config that cannot be loaded (no network, no local copy): only ``hidden_size`` is
+    ever read (reference Cells.py:93, Refinement.py:131).  Module-level so that ``torch.save(model)`` can pickle it."""
+    hidden_size = 768
+
+
 def _bert_config(name):
-    """Only ``hidden_size`` is ever read (reference Cells.py:93, Refinement.py:131)."""
     try:
         from transformers import BertConfig
         return BertConfig.from_pretrained(name)
     except Exception:
-        class _Cfg:
-            hidden_size = 768
-        return _Cfg()
+        return FallbackConfig()
 
 
 class CrossModalAlignment(nn.Module):

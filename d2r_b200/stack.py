@@ -52,6 +52,14 @@ class Stager:
     def __init__(self):
         self._cache: Dict[tuple, tuple] = {}
 
+    def __getstate__(self):
+        # staged copies are derived data: torch.save(model) / copy.deepcopy(model) start with an empty cache
+        return {"_cache": {}}
+
+    def invalidate(self) -> None:
+        """Forget every staged copy (after weights were changed behind autograd's back, e.g. through ``p.data``)."""
+        self._cache.clear()
+
     def get(self, names: Tuple[str, ...], params: Dict[str, Tensor], cd: torch.dtype, suffix: str,
             fresh: Optional[set] = None) -> Tensor:
         ps = [params[n + suffix] for n in names]

@@ -69,6 +69,15 @@ def test_accelerate_keeps_checkpoint_layout_and_matches_reference(models, emulat
     assert abs(loss_a.item() - loss_r.item()) <= 1e-5 * max(1.0, abs(loss_r.item()))
     assert torch.equal(logits_a.argmax(-1), logits_r.argmax(-1))
 
+    # a deep copy of the accelerated model (EMA / best-checkpoint copies) is an independent accelerated model
+    twin = copy.deepcopy(acc)
+    twin.model.itr_module.__dict__["_d2r_graph_cache"] = {"stale": object()}     # never travels with a copy
+    assert "_d2r_graph_cache" not in copy.deepcopy(twin.model.itr_module).__dict__
+    assert twin.model.itr_module.__dict__["_d2r_partner"] is twin.model.Reversed_itr_module
+    with torch.no_grad():
+        assert torch.equal(twin(*batch)[1], logits_a)
+    del twin
+
     # train-mode arithmetic (BatchNorm batch statistics), fp32: same loss, the same parameters receive a gradient
     # (the 110 never-used tensors of SURVEY §8e caveat 3 stay without one) and the gradients agree
     batch = synthetic_batch(4, 32, seed=4, device="cpu")

@@ -330,3 +330,37 @@ def test_emulated_more_than_128_keys(emulated, rev, bf16):
     # gradients: max-norm in fp32; in bf16 this input is the chaotic kind (see above), judged in L2 like the GPU test
     err = (lambda a, b: ((a.double() - b).norm() / b.norm()).item()) if bf16 else relerr
     assert err(t2.grad, t.grad) < tol_g and err(i2.grad, i.grad) < tol_g, (err(t2.grad, t.grad), err(i2.grad, i.grad))
+
+
+def test_emulated_module_copies_and_pickles(emulated):
+    """copy.deepcopy / torch.save of a mirrored module that has already run (train.py keeps state_dicts, but users of
+    the reference also deep-copy models for EMA / best-checkpoint copies): the staged bf16 weights are derived data,
+    not part of either; the copy is independent and gives the same result."""
+    import copy
+    import io
+    from d2r_b200.interaction import InteractionModule
+    P = O.make_params(23, 3, 6)
+    m = InteractionModule(make_args(), 3, 6, 128)
+    m.load_state_dict(P)
+    m.eval()
+    text, image = O.make_inputs(3, 2, 9, 5)
+    text, image = text.bfloat16(), image.bfloat16()
+    with torch.no_grad():
+        o1, _ = m(text, image)
+        m2 = copy.deepcopy(m)
+        assert not m2.__dict__["_d2r_stager"]._cache
+        o2, _ = m2(text, image)
+        assert torch.equal(o1[0], o2[0])
+        for p in m2.parameters():
+            p.mul_(1.5)                                   # version bump -> the copy re-stages, the original does not
+        o3, _ = m2(text, image)
+        o4, _ = m(text, image)
+        assert not torch.equal(o3[0], o4[0]) and torch.equal(o4[0], o1[0])
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        assert len(buf.getvalue()) < 1.02 * sum(p.numel() * 4 for p in m.parameters()) + (1 << 20)
+        buf.seek(0)
+        m3 = torch.load(buf, weights_only=False)
+        o5, _ = m3(text, image)
+        assert torch.equal(o5[0], o1[0])
+        assert not [k for k in m.state_dict() if "_d2r" in k]
