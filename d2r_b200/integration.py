@@ -13,7 +13,10 @@ stays the reference's stock PyTorch, as BASELINE.json:north_star asks):
                                              subclasses: the first call computes both, the second returns its half
   ``text_pool`` / ``vision_pool``            :778-779, :871-872 (BertPooler on row 0 of the stack outputs)
   ``block_fusion``                           :776, :884 (XModules.Block bilinear fusion)
-  ``js_div``                                 :849 (XModules.js_div on sim_paths / Reversed_sim_paths)
+  ``js_div``                                 :849 (XModules.js_div on sim_paths / Reversed_sim_paths): the module-level
+                                             symbol :849 resolves becomes a dispatcher that takes the fused kernel only
+                                             while an ACCELERATED backbone's forward is running -- other models of the
+                                             same class in the process keep the reference's own function
 
 The swapped-in modules are bound to the SAME ``nn.Parameter`` / buffer objects as the modules they replace (no
 copy): ``state_dict`` keys, optimizer parameter groups built by name (modules/train.py:293-320) and checkpoints
@@ -22,6 +25,7 @@ copy): ``state_dict`` keys, optimizer parameter groups built by name (modules/tr
 from __future__ import annotations
 
 import sys
+import threading
 
 import torch
 import torch.nn as nn
@@ -132,6 +136,28 @@ def _rebind(new: nn.Module, old: nn.Module) -> nn.Module:
     return new
 
 
+_js_scope = threading.local()      # depth of accelerated backbone forwards running on this thread
+
+
+def _js_dispatcher(original):
+    """Stand-in for the reference module's global ``js_div``: fused kernel inside an accelerated backbone's forward,
+    the reference's own function everywhere else."""
+    def js_div_dispatch(*args, **kwargs):
+        if getattr(_js_scope, "depth", 0) > 0:
+            return js_div(*args, **kwargs)
+        return original(*args, **kwargs)
+    js_div_dispatch._d2r_original = original
+    return js_div_dispatch
+
+
+def _js_enter(module, args):
+    _js_scope.depth = getattr(_js_scope, "depth", 0) + 1
+
+
+def _js_exit(module, args, output):
+    _js_scope.depth = max(0, getattr(_js_scope, "depth", 0) - 1)
+
+
 def _find_backbone(model: nn.Module) -> nn.Module:
     for m in model.modules():
         if hasattr(m, "itr_module") and hasattr(m, "Reversed_itr_module"):
@@ -171,6 +197,10 @@ def accelerate(model: nn.Module, *, pair: bool = True, head: bool = True, graph:
         bb.block_fusion = _rebind(new, old)
         mod = sys.modules.get(type(bb).__module__)
         if mod is not None and hasattr(mod, "js_div"):
-            mod.js_div = js_div          # the symbol modeling_unimo.py:849 resolves at call time
+            if not hasattr(mod.js_div, "_d2r_original"):
+                mod.js_div = _js_dispatcher(mod.js_div)      # the symbol modeling_unimo.py:849 resolves at call time
+            if "_d2r_js_hooks" not in bb.__dict__:
+                bb.__dict__["_d2r_js_hooks"] = (bb.register_forward_pre_hook(_js_enter),
+                                                bb.register_forward_hook(_js_exit, always_call=True))
     model.__dict__["_d2r_accelerated"] = dict(pair=pair, head=head, graph=bool(graph and pair))
     return model

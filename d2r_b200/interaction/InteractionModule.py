@@ -14,6 +14,21 @@ from .DynamicInteraction import (DynamicInteraction_Layer, DynamicInteraction_La
                                  Reversed_DynamicInteraction_Layer, Reversed_DynamicInteraction_Layer0)
 
 
+def _check_inputs(mod, text, image):
+    """The reference fails on these inputs somewhere inside its first matmul (RuntimeError); fail at the boundary, with
+    the same exception type and a message that names the argument."""
+    D = mod.args.embed_size
+    for name, t in (("text", text), ("image", image)):
+        if t.dim() != 3 or t.shape[-1] != D:
+            raise RuntimeError(f"d2r_b200.{type(mod).__name__}: the {name} input must be [batch, tokens, {D}], "
+                               f"got {tuple(t.shape)}")
+        if t.shape[1] == 0:
+            raise RuntimeError(f"d2r_b200.{type(mod).__name__}: the {name} input has no tokens")
+    if text.shape[0] != image.shape[0] or text.shape[0] == 0:
+        raise RuntimeError(f"d2r_b200.{type(mod).__name__}: batch sizes differ or are zero "
+                           f"({text.shape[0]} and {image.shape[0]})")
+
+
 def _stack_request(mod, own, ctx):
     R, Kc = mod.num_layer_routing, mod.num_cells
     heads = mod.dynamic_itr_l0.imrc.sa.h
@@ -53,6 +68,7 @@ def run_pair(itr_module, reversed_itr_module, text, image, return_path_probs=Fal
     self.Reversed_itr_module, text, image)``.  The two stacks are independent until the loss, so they are
     issued on two CUDA streams inside one autograd node (forward and backward): on B200 the tail waves and the
     many small launches of one stack are filled by the other.  Results are identical to the two separate calls."""
+    _check_inputs(itr_module, text, image)
     rt, ri = run_blocks([_stack_request(itr_module, text, image), _stack_request(reversed_itr_module, image, text)])
     return _stack_result(itr_module, rt, return_path_probs), _stack_result(reversed_itr_module, ri, return_path_probs)
 
@@ -74,6 +90,7 @@ class InteractionModule(nn.Module):
         self.bn = nn.BatchNorm1d(args.embed_size)              # constructed but unused upstream (:20)
 
     def forward(self, text, image, return_path_probs=False):
+        _check_inputs(self, text, image)
         return _stack_call(self, text, image, return_path_probs)
 
 
@@ -95,4 +112,5 @@ class Reversed_InteractionModule(nn.Module):
 
     def forward(self, text, image, return_path_probs=False):
         # the image stream is this branch's own stream, the text is the context (reference :157-165)
+        _check_inputs(self, text, image)
         return _stack_call(self, image, text, return_path_probs)

@@ -73,6 +73,16 @@ def test_envelope_errors():
     m = InteractionModule(make_args(), 2, 4, 128)
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(torch.randn(2, 4, 768), torch.randn(2, 3, 768))
+    # malformed inputs: RuntimeError like the reference (which fails inside its first matmul), raised at the boundary
+    from d2r_b200.interaction import Reversed_InteractionModule, run_pair
+    r = Reversed_InteractionModule(make_args(), 2, 4, 128)
+    for text, image, what in ((torch.randn(2, 4, 512), torch.randn(2, 3, 512), "text input must be"),
+                              (torch.randn(2, 4, 768), torch.randn(3, 3, 768), "batch sizes"),
+                              (torch.randn(4, 768), torch.randn(3, 768), "text input must be"),
+                              (torch.randn(2, 4, 768), torch.randn(2, 0, 768), "image input has no tokens")):
+        for call in (lambda: m(text, image), lambda: r(text, image), lambda: run_pair(m, r, text, image)):
+            with pytest.raises(RuntimeError, match=what):
+                call()
 
 
 def test_dead_parameter_plan_matches_reference_fixture():
