@@ -222,22 +222,32 @@ def test_config2_train_vs_oracle(B, bf16):
     r2 = oracle_run(Pi, text, image, R, True, True)
     tol_p, tol_o = (2e-2, 5e-2) if bf16 else (2e-5, 1e-4)
     rep = {}
-    for tag, (o, s, p), r in (("text", (o1, s1, p1), r1), ("image", (o2, s2, p2), r2)):
-        ep = max(relerr(a, b) for a, b in zip(p, r[2]))
+    a1 = a2 = None
+    if bf16:
+        # yardstick: the reference algorithm's own bf16 mode (oracle under CPU autocast) against its fp32 run.
+        # Measured at B = 64 (CPU, round 2): its outputs deviate 5.0-5.5e-2 in max-norm (1.1-1.3e-2 in L2), its routing
+        # probabilities 8e-3; this library: 3.5-4.7e-2 (7e-3), 7e-5.
+        a1 = oracle_run(Pt, text, image, R, False, True, autocast=True)
+        a2 = oracle_run(Pi, text, image, R, True, True, autocast=True)
+    for tag, (o, s, p), r, a in (("text", (o1, s1, p1), r1, a1), ("image", (o2, s2, p2), r2, a2)):
+        ep = max(relerr(a_, b_) for a_, b_ in zip(p, r[2]))
         rep[tag] = dict(probs=ep, sim=relerr(s, r[1]), out=relerr(o, r[0]), out_l2=l2rel(o, r[0]))
+        y_out = y_l2 = 0.0
+        if a is not None:
+            y_out, y_l2 = relerr(a[0], r[0]), l2rel(a[0], r[0])
+            rep[tag].update(ref_autocast_out=y_out, ref_autocast_out_l2=y_l2)
         assert ep <= tol_p, (tag, "probs", ep)
         assert relerr(s, r[1]) <= 2 * tol_p, (tag, "sim", relerr(s, r[1]))
-        assert relerr(o, r[0]) <= tol_o, (tag, "out", relerr(o, r[0]))
+        # outputs: the stated bound, or 1.5 x what the reference's own bf16 mode does on this input if that is larger
+        assert relerr(o, r[0]) <= max(tol_o, 1.5 * y_out), (tag, "out", relerr(o, r[0]), y_out)
+        if bf16:
+            assert l2rel(o, r[0]) <= max(2e-2, 1.5 * y_l2), (tag, "out l2", l2rel(o, r[0]), y_l2)
     # gradients: d_text / d_image receive contributions from BOTH stacks
     ref_dt, ref_di = r1[3] + r2[3], r1[4] + r2[4]
     e_t, e_i = l2rel(t.grad, ref_dt), l2rel(i.grad, ref_di)
     rep["input_grads"] = dict(d_text_l2rel=e_t, d_image_l2rel=e_i, cos=min(cosine(t.grad, ref_dt), cosine(i.grad, ref_di)))
-    a1 = a2 = None
     y_in = 0.0
     if bf16:
-        # yardstick: the reference algorithm's own bf16 mode (oracle under CPU autocast) against its fp32 run
-        a1 = oracle_run(Pt, text, image, R, False, True, autocast=True)
-        a2 = oracle_run(Pi, text, image, R, True, True, autocast=True)
         y_in = max(l2rel(a1[3] + a2[3], ref_dt), l2rel(a1[4] + a2[4], ref_di))
         rep["input_grads"]["ref_autocast_l2rel"] = y_in
     try:
