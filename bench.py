@@ -512,7 +512,7 @@ def full_arm(args):
     import torch.distributed as dist
     from baseline.full_model import build_reference_model, synthetic_batch
     from d2r_b200 import kernels as K
-    from d2r_b200.dp import BucketedGradReducer
+    from d2r_b200.dp import BucketedGradReducer, FlatGradReducer
     from d2r_b200.integration import accelerate
     cfg = CONFIGS["full"]
     rank = int(os.environ.get("RANK", "0"))
@@ -589,12 +589,22 @@ def full_arm(args):
         graphed = False
         fwd_bwd(devb)
         torch.cuda.synchronize()
-    # gradients live in one flat buffer from here on; its buckets are all-reduced from inside the backward
-    reducer = BucketedGradReducer(model.parameters(), bucket_mb=128.0)
-    reducer.plan()
+    # Default: FlatGradReducer -- one packing copy + one all-reduce of the live gradients after the backward (the
+    # variant measured on the GPU at N = 1 and N = 2).  --bucketed-allreduce: gradients are views of one flat buffer and
+    # bucket all-reduces are launched by hooks from inside the backward (gloo-tested; on the GPU only run at N = 1).
+    bucketed = bool(getattr(args, "bucketed_allreduce", False))
+    if bucketed:
+        reducer = BucketedGradReducer(model.parameters(), bucket_mb=128.0)
+        reducer.plan()
+    else:
+        reducer = FlatGradReducer(model.parameters())
     h_loss = torch.empty(1).pin_memory()
 
     def fwd_bwd_dp(batch):
+        if not bucketed:
+            loss = fwd_bwd(batch)
+            reducer.step()
+            return loss
         reducer.begin_step()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss, logits = model(*batch)
@@ -624,7 +634,8 @@ def full_arm(args):
     ms_e2e = time_steps(lambda: step(True), args.steps, 2)
     # share of the routed stacks in the step: the two stacks alone, same batch, same precision
     ms_stack = None
-    reducer.remove()                  # (no collectives from the rank-0-only measurement below)
+    if bucketed:
+        reducer.remove()              # (no collectives from the rank-0-only measurement below)
     if rank == 0:
         bb = model.model
         t_in = torch.randn(B, cfg["Lt"], D, device=dev, requires_grad=True)
@@ -657,8 +668,9 @@ def full_arm(args):
             "dtype": "bf16", "data": "synthetic", "config": workload_config("full", world, B),
             "engine": {"cuda_graph": "the two stacks (forward graph + backward graph); encoders eager" if graphed else False,
                        "swap": "d2r_b200.integration.accelerate (stacks via run_pair, CLS poolers, Block fusion, js_div)",
-                       "allreduce": f"{len(reducer.buckets)} buckets of one flat fp32 gradient buffer, all-reduced from "
-                                    f"inside the backward; {reducer.dead} never-used tensors excluded",
+                       "allreduce": (f"{len(reducer.buckets)} buckets of one flat fp32 gradient buffer, all-reduced from "
+                                     f"inside the backward; {reducer.dead} never-used tensors excluded") if bucketed
+                       else f"one flat fp32 bucket per step, {reducer.dead} never-used tensors excluded",
                        "parameters_M": nparams / 1e6},
             "clocks": clocks,
             "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
@@ -958,6 +970,9 @@ def main():
                          "(GradAllReducer.install), captured in the CUDA graph")
     ap.add_argument("--no-overlap-allreduce", action="store_true",
                     help="one gradient all-reduce per step, issued after the graph replay (round-1 behaviour)")
+    ap.add_argument("--bucketed-allreduce", action="store_true",
+                    help="--config full: BucketedGradReducer (bucket all-reduces launched by hooks from inside the "
+                         "backward) instead of one flat all-reduce after it")
     ap.add_argument("--aux-wgrad", action="store_true", help="weight-gradient GEMMs on the helper stream as well")
     ap.add_argument("--no-aux-bias", action="store_true",
                     help="bias-gradient column sums on the GEMMs' own stream instead of a helper stream")
