@@ -123,7 +123,10 @@ def run_reference_subprocess(device, batch, steps, warmup, cfg, bf16=False, time
     env = dict(os.environ)
     if device == "cpu":
         env["CUDA_VISIBLE_DEVICES"] = ""
-    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+    # the arm must not inherit a launcher's rank variables or its thread caps (torchrun exports OMP_NUM_THREADS=1)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "GROUP_RANK",
+              "ROLE_RANK", "LOCAL_WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS",
+              "GOMP_CPU_AFFINITY", "KMP_AFFINITY"):
         env.pop(k, None)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     if out.returncode != 0:
@@ -443,8 +446,11 @@ def own_arm(args):
         graph_used = graph is not None
         graph = static_loss = None            # release the graph's private pool before the stock-PyTorch run
         torch.cuda.empty_cache()
-        cpu = cpu_baseline(cfg, steps=5, warmup=1)
-        stock = stock_pytorch_b200(cfg, B)
+        # the two baselines are measured at N = 1 only (rank 0 would keep N - 1 GPUs idle for a minute or two; and under
+        # torchrun the CPU arm inherits the rank's restricted CPU affinity: 0.3-0.4 samples/s instead of 25 in round 2)
+        skipped = {"value": None, "skipped": "measured at --gpus 1 only"}
+        cpu = cpu_baseline(cfg, steps=5, warmup=1) if world == 1 else dict(skipped)
+        stock = stock_pytorch_b200(cfg, B) if world == 1 else dict(skipped)
         if stock and stock.get("value"):
             stock["speedup_of_this_repo"] = value / world / stock["value"]      # per GPU vs one B200
         line = {
@@ -686,7 +692,8 @@ def full_arm(args):
                          "frac": value / world * 3 * 52.5e9 / 1e12 / load_peaks().get("bf16_tflops_sustained", 1400.0),
                          "traffic": None},
             "stock_pytorch_b200": stock,
-            "cpu_baseline": cpu_baseline(cfg, steps=3, warmup=1),
+            "cpu_baseline": cpu_baseline(cfg, steps=3, warmup=1) if world == 1
+            else {"value": None, "skipped": "measured at --gpus 1 only"},
         }
         emit(line)
     if world > 1:
@@ -798,7 +805,7 @@ def eval_sweep(args, cfg, mt, mi, dev, rank, world, local):
         fl = useful_flops_per_sample(LT, LI, R)
         for p in ok:
             p["frac_of_tensor_peak"] = p["samples_per_s"] / world * fl / 1e12 / tc_peak
-        cpu = cpu_baseline(cfg, steps=5, warmup=1)
+        cpu = cpu_baseline(cfg, steps=5, warmup=1) if world == 1 else {"value": None, "skipped": "measured at --gpus 1 only"}
         line = {"metric": metric_name("eval-sweep"), "value": best["samples_per_s"],
                 "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
