@@ -50,8 +50,11 @@ def _fwd_one(spec, tensors):
     env.bn_modes = spec[11]
     x_cd = [None if t is None else t.detach().to(cd).contiguous() for t in inputs]
     outs, state = fwd(env, x_cd)
+    # the state aliases inputs and parameters instead of going through ctx.save_for_backward: keep autograd's safety
+    # net by hand -- their version counters are compared again when the backward starts
     rec = dict(spec=spec, state=state, in_dtypes=[None if t is None else t.dtype for t in inputs],
-               out_meta=[(o.shape, o.dtype) for o in outs])
+               out_meta=[(o.shape, o.dtype) for o in outs],
+               versions=[(t, t._version) for t in tensors if t is not None])
     return tuple(outs), rec
 
 
@@ -123,6 +126,14 @@ class _BlocksFn(torch.autograd.Function):
         if recs is None:
             raise RuntimeError("d2r_b200: trying to backward through the stack a second time -- the saved "
                                "activations are freed by the first backward (retain_graph is not supported)")
+        for rec in recs:                 # before any launch or stream fork
+            for t, version in rec["versions"]:
+                if t._version != version:
+                    raise RuntimeError("d2r_b200: one of the variables needed for gradient computation (an input or a "
+                                       f"parameter of the stack, shape {tuple(t.shape)}) has been modified by an "
+                                       f"inplace operation: it is at version {t._version}, the forward saw version "
+                                       f"{version}")
+            rec["versions"] = None
         with _device_guard(ctx.dev):
             # atomically-accumulated gradients (bias, router head, SAF) are carved out of per-stream zeroed arenas:
             # start every backward -- of the whole stack or of a stand-alone cell / Block -- with fresh ones, so that

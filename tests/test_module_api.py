@@ -105,6 +105,42 @@ def test_shard_batch():
         assert max(sizes) - min(sizes) <= 1
 
 
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _run_world2(worker, attempts=3):
+    """Spawn two gloo ranks of ``worker(rank, world, port, queue)`` on 127.0.0.1 -> their results sorted by rank.  The
+    rendezvous port is OS-assigned; a failed rendezvous (port taken in the meantime, a loaded host) is retried."""
+    import queue as _queue
+    import torch.multiprocessing as mp
+    last = None
+    for _ in range(attempts):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        try:
+            res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+            for p in procs:
+                p.join(timeout=60)
+            if all(p.exitcode == 0 for p in procs):
+                return res
+            last = RuntimeError(f"worker exit codes {[p.exitcode for p in procs]}")
+        except _queue.Empty as e:
+            last = e
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+            p.join(timeout=10)
+    raise AssertionError(f"world-2 gloo run failed {attempts} times: {last!r}")
+
+
 def _dp_worker(rank, world, port, q):
     import torch.distributed as dist
     from d2r_b200.dp import GradAllReducer, shard_batch
@@ -135,17 +171,7 @@ def _dp_worker(rank, world, port, q):
 
 def test_dp_allreduce_gloo_world2():
     """N-rank DP == mean of the per-shard gradients (world_size 2, gloo, CPU)."""
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_world2(_dp_worker)
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     torch.manual_seed(0)
     lin = torch.nn.Linear(6, 3)
@@ -225,17 +251,7 @@ def _dp_layerwise_worker(rank, world, port, q):
 
 
 def test_dp_layerwise_allreduce_gloo_world2():
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_dp_layerwise_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_world2(_dp_layerwise_worker)
     assert res[0][1] == res[1][1]                     # both ranks hold the same averaged bucket
     assert res[0][2] and res[1][2]
 
@@ -283,17 +299,7 @@ def _dp_bucketed_worker(rank, world, port, q):
 
 
 def test_dp_bucketed_overlapped_allreduce_gloo_world2():
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 33500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_dp_bucketed_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_world2(_dp_bucketed_worker)
     torch.manual_seed(3)
     model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
                                 torch.nn.Linear(16, 3))

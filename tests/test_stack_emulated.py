@@ -364,3 +364,31 @@ def test_emulated_module_copies_and_pickles(emulated):
         o5, _ = m3(text, image)
         assert torch.equal(o5[0], o1[0])
         assert not [k for k in m.state_dict() if "_d2r" in k]
+
+
+def test_emulated_inplace_modification_between_forward_and_backward_is_detected(emulated):
+    """The saved state aliases inputs and parameters (no ctx.save_for_backward): the version counters are checked by
+    hand when the backward starts, with autograd's own wording."""
+    from d2r_b200.interaction import InteractionModule
+    m = InteractionModule(make_args(), 3, 6, 128)
+    m.load_state_dict(O.make_params(23, 3, 6))
+    text, image = O.make_inputs(3, 2, 9, 5)
+
+    def forward():
+        t, i = (text * 1.0).requires_grad_(True), (image * 1.0).requires_grad_(True)
+        t2, i2 = t * 1.0, i * 1.0                     # non-leaf inputs, as the encoders' outputs are
+        out, sim = m(t2, i2)
+        return t2, i2, out[0].sum() + sim.sum()
+
+    t2, i2, loss = forward()
+    with torch.no_grad():
+        i2.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        loss.backward()
+    t2, i2, loss = forward()
+    with torch.no_grad():
+        m.dynamic_itr_l0.imrc.sa.feed_forward_layer.fc1.weight.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        loss.backward()
+    t2, i2, loss = forward()
+    loss.backward()                                  # untouched: fine
