@@ -61,12 +61,13 @@ CONFIGS = {
 }
 SWEEP_BATCHES = (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096)
 # DRAM traffic of the dominant launches from `ncu --set full` captures (see profiles/): per launch, like `achieved`
-GEMM_TRAFFIC_BYTES = 62.0e6
-GEMM_TRAFFIC_NOTE = ("dram__bytes_read+write of one m=32768 n=768 k=768 launch (the K=768 projections are 60% of the "
-                     "GEMM time); 101.8 MB algorithmic operand bytes; profiles/r01_ncu_gemm_k768_pair.txt")
-AGG_TRAFFIC_BYTES = 461.3e6
-AGG_TRAFFIC_NOTE = ("agg_fwd_kernel text non-final launch: 503.3 MB algorithmic, 461.3 MB dram "
-                    "(profiles/r01_ncu_agg_fwd.txt)")
+GEMM_TRAFFIC_BYTES = 62.3e6
+GEMM_TRAFFIC_NOTE = ("dram__bytes_read+write of one m=32768 n=768 k=768 launch (51.6 MB read + 10.7 MB written; the K=768 "
+                     "projections are 60% of the GEMM time); 101.8 MB algorithmic operand bytes, the output is mostly "
+                     "still in L2 at kernel end; profiles/r02_ncu_gemm_k768_pair.txt")
+AGG_TRAFFIC_BYTES = 454.6e6
+AGG_TRAFFIC_NOTE = ("agg_fwd_kernel text non-final launch: 503.3 MB algorithmic, 454.6 MB dram (203.0 read + 251.6 "
+                    "written); agg_bwd_kernel: 704.6 MB algorithmic, 687.5 MB dram (profiles/r02_ncu_agg_fwd_bwd.txt)")
 CPU_SAMPLE_BATCH = 8
 
 
