@@ -130,3 +130,59 @@ def test_reference_derived_shapes(K, R):
     out, sim, probs = O.stack_forward(P, text, image, R, K, False, False)
     assert out[0].shape == (3, 8, 768) and sim.shape == (3, 3)
     assert sum(p[0].numel() for p in probs) == K * K * (R - 1) + K
+
+
+@pytest.mark.parametrize("name,seed,rev", [("bench_text_b8", 2023, False), ("bench_image_b8", 2024, True)])
+def test_oracle_matches_reference_at_the_benchmark_token_counts(name, seed, rev):
+    """The oracle pinned at BASELINE configs[0]/[1] token counts (128 text + 50 image tokens, R = 3, K = 6, batch 8,
+    train mode, bench.py's seeds and loss) on digests generated by the unmodified reference
+    (tests/golden/make_benchshape_golden.py): the GPU parity tests at this shape compare with the oracle."""
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    B, Lt, Li, R = 8, 128, 50, 3
+    torch.set_num_threads(os.cpu_count() or 8)
+    P = O.make_params(seed, R, 6)
+    for k, v in P.items():
+        if v.is_floating_point() and "running" not in k and not O.is_dead_param(k):
+            v.requires_grad_(True)
+    text, image = O.make_inputs(2023, B, Lt, Li)
+    text.requires_grad_(True)
+    image.requires_grad_(True)
+    out, sim, probs = O.stack_forward(P, text, image, R, 6, rev, True, {})
+    loss = out[0].sum() + sim.sum()
+    loss.backward()
+
+    def dg(t, n):
+        f = t.detach().double().flatten()
+        idx = torch.linspace(0, f.numel() - 1, n).long()
+        return torch.cat([f.sum().view(1), f.abs().sum().view(1), f[idx]]).numpy()
+
+    def close(got, ref, tol, what):
+        assert abs(got[1] - ref[1]) <= tol * abs(ref[1]), (what, "abs-sum", got[1], ref[1])
+        assert np.abs(got[2:] - ref[2:]).max() <= tol * np.abs(ref[2:]).max() + 1e-9, (what, "samples")
+
+    assert abs(loss.item() - float(gold["loss"])) <= 2e-5 * abs(float(gold["loss"]))
+    np.testing.assert_allclose(sim.detach().numpy(), gold["sim"], rtol=2e-5, atol=2e-6)
+    for i, p in enumerate(probs):
+        np.testing.assert_allclose(p.detach().numpy(), gold[f"probs{i}"], rtol=1e-5, atol=1e-7)
+    close(dg(out[0], 256), gold["out"], 2e-5, "out")
+    # (fp32 rounding of the backward at this shape: tools/yardsticks.py measures 3e-4 in L2 between the oracle's own
+    #  fp32 and float64 runs, single elements up to 1.5e-3)
+    close(dg(text.grad, 256), gold["d_text"], 5e-3, "d_text")
+    close(dg(image.grad, 256), gold["d_image"], 5e-3, "d_image")
+    dead = set(gold["dead"].tolist())
+    worst = ("", 0.0)
+    for k, v in P.items():
+        if not v.requires_grad and not (v.is_floating_point() and "running" not in k):
+            continue
+        if k in dead:
+            assert O.is_dead_param(k) and v.grad is None, k
+            continue
+        if not v.is_floating_point() or "running" in k:
+            continue
+        if O.is_zero_grad_param(k, True):      # mathematically zero (softmax shift / BatchNorm shift invariance): noise
+            continue
+        got, ref = dg(v.grad, 16), gold["gd/" + k]
+        e = abs(got[1] - ref[1]) / abs(ref[1])
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] <= 5e-3, worst
