@@ -1,5 +1,6 @@
 """Benchmark-shape fixtures from the UNMODIFIED reference (BASELINE configs[0] / configs[1] token counts: 128 text +
-50 image tokens, K = 6, R = 3, batch 8, train mode), digests only so that the files stay small.
+50 image tokens, K = 6, R = 3, batch 8; and configs[3]: R = 4, 256 + 197 tokens, batch 2; train mode), digests only so
+that the files stay small.
 
 Run (only where /root/reference exists):  python tests/golden/make_benchshape_golden.py
 
@@ -29,8 +30,9 @@ sys.path.insert(0, REF)
 from oracle import d2r_oracle as O  # noqa: E402
 from tests.golden.make_golden import ref_args  # noqa: E402
 
-B, LT, LI, R = 8, 128, 50, 3
-CASES = [("bench_text_b8", 2023, False), ("bench_image_b8", 2024, True)]
+# name, parameter seed, reversed, B, Lt, Li, R   (the deep_* cases: BASELINE configs[3], R = 4, 256 + 197 tokens)
+CASES = [("bench_text_b8", 2023, False, 8, 128, 50, 3), ("bench_image_b8", 2024, True, 8, 128, 50, 3),
+         ("deep_text_b2", 2023, False, 2, 256, 197, 4), ("deep_image_b2", 2024, True, 2, 256, 197, 4)]
 
 
 def digest(t, n):
@@ -43,7 +45,7 @@ def main():
     from models.InteractionModule import InteractionModule, Reversed_InteractionModule
     args = ref_args(tempfile.mkdtemp())
     torch.set_num_threads(os.cpu_count() or 8)
-    for name, seed, rev in CASES:
+    for name, seed, rev, B, LT, LI, R in CASES:
         torch.manual_seed(0)
         m = (Reversed_InteractionModule if rev else InteractionModule)(args, num_layer_routing=R, num_cells=6, path_hid=128)
         m.load_state_dict(O.make_params(seed, R, 6))

@@ -132,13 +132,15 @@ def test_reference_derived_shapes(K, R):
     assert sum(p[0].numel() for p in probs) == K * K * (R - 1) + K
 
 
-@pytest.mark.parametrize("name,seed,rev", [("bench_text_b8", 2023, False), ("bench_image_b8", 2024, True)])
-def test_oracle_matches_reference_at_the_benchmark_token_counts(name, seed, rev):
+@pytest.mark.parametrize("name,seed,rev,B,Lt,Li,R", [("bench_text_b8", 2023, False, 8, 128, 50, 3),
+                                                      ("bench_image_b8", 2024, True, 8, 128, 50, 3),
+                                                      ("deep_text_b2", 2023, False, 2, 256, 197, 4),
+                                                      ("deep_image_b2", 2024, True, 2, 256, 197, 4)])
+def test_oracle_matches_reference_at_the_benchmark_token_counts(name, seed, rev, B, Lt, Li, R):
     """The oracle pinned at BASELINE configs[0]/[1] token counts (128 text + 50 image tokens, R = 3, K = 6, batch 8,
-    train mode, bench.py's seeds and loss) on digests generated by the unmodified reference
+    train mode, bench.py's seeds and loss; and configs[3]: R = 4, 256 + 197 tokens) on digests generated by the unmodified reference
     (tests/golden/make_benchshape_golden.py): the GPU parity tests at this shape compare with the oracle."""
     gold = np.load(os.path.join(GOLD, name + ".npz"))
-    B, Lt, Li, R = 8, 128, 50, 3
     torch.set_num_threads(os.cpu_count() or 8)
     P = O.make_params(seed, R, 6)
     for k, v in P.items():
